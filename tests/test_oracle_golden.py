@@ -1,0 +1,113 @@
+"""CPU: pin the oracle (oracle/gq_oracle.c) to vectors produced by the reference itself
+(tests/golden/make_golden.py ran quant/gptq/src of the reference on CPU)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+TYPES = {"Q2_K": 10, "Q3_K": 11, "Q4_K": 12, "Q5_K": 13, "Q6_K": 14}
+KEYS = ["qweight", "d", "sq", "dmin", "zq"]
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _U(g):
+    # stored as U^T contiguous == the reference's column-major U; hand the oracle the strided view
+    return g["U_colmajor_T"].T
+
+
+def _five_raw(o):
+    return dict(qweight=o[0], d=o[1].view(np.uint16), sq=o[2], dmin=o[3].view(np.uint16), zq=o[4])
+
+
+@pytest.mark.parametrize("case", ["b1_a.npz", "b1_b.npz"])
+@pytest.mark.parametrize("tname", list(TYPES))
+def test_step_matches_reference_bit_exact(golden_dir, case, tname):
+    g = _load(golden_dir, case)
+    o = orc.gptq_step(g["W"], _U(g), TYPES[tname], block_size=int(g["block_size"]))
+    got = _five_raw(o)
+    for k in KEYS:
+        ref = g[f"{tname}_ieee_{k}"]
+        assert got[k].dtype == ref.dtype and got[k].shape == ref.shape, k
+        assert np.array_equal(got[k], ref), f"{case} {tname} {k}"
+    # w written back by the reference loop == dequantize_linear_weight of its outputs
+    assert np.array_equal(o[5], g[f"{tname}_ieee_dequant"])
+    # unpatched reference (torch's non-IEEE sqrt): report, require >= 95% identical rows
+    bad = np.zeros(g["W"].shape[0], bool)
+    for k in KEYS:
+        bad |= (got[k] != g[f"{tname}_raw_{k}"]).reshape(bad.size, -1).any(1)
+    assert bad.mean() <= 0.05
+
+
+@pytest.mark.parametrize("case", ["b1_a.npz", "b1_b.npz"])
+@pytest.mark.parametrize("tname", list(TYPES))
+def test_pack_and_dequant_match_reference(golden_dir, case, tname):
+    g = _load(golden_dir, case)
+    five = [g[f"{tname}_ieee_{k}"] for k in KEYS]
+    five[1] = five[1].view(np.float16)
+    five[3] = five[3].view(np.float16)
+    packed = orc.pack(TYPES[tname], *five)
+    assert np.array_equal(packed, g[f"{tname}_ieee_packed"])
+    deq = orc.dequantize(TYPES[tname], *five)
+    assert np.array_equal(deq, g[f"{tname}_ieee_dequant"])
+
+
+@pytest.mark.parametrize("tname", list(TYPES))
+def test_packed_bytes_decode_with_gguf_py(golden_dir, tname):
+    """independent cross-check: gguf-py's dequantize of the packed bytes == the reference dequant."""
+    gguf = pytest.importorskip("gguf")
+    g = _load(golden_dir, "b1_a.npz")
+    five = [g[f"{tname}_ieee_{k}"] for k in KEYS]
+    five[1] = five[1].view(np.float16)
+    five[3] = five[3].view(np.float16)
+    packed = orc.pack(TYPES[tname], *five)
+    deq = gguf.quants.dequantize(packed, gguf.GGMLQuantizationType(TYPES[tname]))
+    assert np.array_equal(deq.astype(np.float32), g[f"{tname}_ieee_dequant"])
+
+
+@pytest.mark.parametrize("tname", list(TYPES))
+def test_search_edge_cases(golden_dir, tname):
+    g = _load(golden_dir, "search_edge.npz")
+    d, sq, dmin, zq = orc.get_scale_and_zero(g["x"], TYPES[tname])
+    assert np.array_equal(d.view(np.uint16), g[f"{tname}_ieee_d"])
+    assert np.array_equal(dmin.view(np.uint16), g[f"{tname}_ieee_dmin"])
+    assert np.array_equal(sq, g[f"{tname}_ieee_sq"])
+    assert np.array_equal(zq, g[f"{tname}_ieee_zq"])
+
+
+@pytest.mark.parametrize("tname", list(TYPES))
+def test_rtn_matches_reference(golden_dir, tname):
+    g = _load(golden_dir, "rtn.npz")
+    got = _five_raw(orc.rtn_quantize(g["W"], TYPES[tname]))
+    for k in KEYS:
+        assert np.array_equal(got[k], g[f"{tname}_ieee_{k}"]), k
+
+
+def test_large_validation_was_clean(golden_dir):
+    """make_golden.py's 1024x1024 oracle-vs-reference run (not stored) must have had 0 mismatching rows."""
+    s = json.load(open(os.path.join(golden_dir, "golden_stats.json")))
+    for t, row in s["oracle_vs_reference_1024x1024"].items():
+        assert row["ieee"]["mismatching_rows"] == 0, t
+
+
+def test_prepare_factorisation_properties():
+    rng = np.random.default_rng(0)
+    n, d_row = 96, 8
+    X = rng.standard_normal((400, n)).astype(np.float32)
+    H = np.zeros((n, n), np.float32)
+    orc.hessian_update(H, X, 0.0, 2.0)
+    assert np.allclose(H, 2.0 * X.T.astype(np.float64) @ X.astype(np.float64), rtol=1e-5, atol=1e-4)
+    W = rng.standard_normal((d_row, n)).astype(np.float32)
+    W[:, 3] = 0.0
+    U, Hd, Wm, bad = orc.prepare(H, W, 0.01)
+    assert not bad
+    assert np.allclose(np.tril(U, -1), 0)
+    inv = np.linalg.inv(Hd.astype(np.float64))
+    assert np.allclose(U.T.astype(np.float64) @ U.astype(np.float64), inv, rtol=1e-3, atol=1e-6)
+
+    assert np.all(Hd[3, :3] == 0) and np.all(Hd[:3, 3] == 0)
