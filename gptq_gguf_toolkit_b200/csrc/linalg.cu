@@ -1,0 +1,279 @@
+// linalg.cu -- the dense linear algebra either side of the column loop:
+//   gq_hessian_update  (replaces GPTQ.update's H.addmm_, quant/gptq/src/gptq.py:108-112)
+//   gq_pre_step        (replaces quantization_pre_step's dead-channel fix, gptq.py:134-141)
+//   gq_prepare         (replaces GPTQ._prepare + inv_sym, gptq.py:305-324, linalg_utils.py:8-12)
+//
+// gq_prepare does NOT mirror the reference's potrf -> potri -> potrf chain (4n^3/3 flops).  With J the
+// index reversal, H = R R^T (R upper)  <=>  J H J = L L^T (L lower, L = J R J), and
+// chol(inv(H), upper) = R^-1 = J L^-1 J by uniqueness of the Cholesky factor.  So: one blocked Cholesky of
+// the reversed matrix plus one blocked triangular inverse (2n^3/3 flops), then a reversed copy.
+// The triangular inverse is a log-depth pairwise merge  inv([[A,0],[C,B]]) = [[Ai,0],[-Bi C Ai, Bi]],
+// whose work is all GEMM (zero tiles of the triangular factors are skipped).
+#include "sgemm.cuh"
+
+namespace {
+
+constexpr int NB = 128;   // panel width
+
+// ---------------------------------------------------------------------------------------------
+// masks and damping
+// ---------------------------------------------------------------------------------------------
+// W[:, j] = 0 where H[j][j] == 0 (gptq.py:134,141).  Runs BEFORE fix_dead_diag (stream order).
+__global__ void zero_dead_cols_kernel(const float *__restrict__ H, float *W, int d_row, int d_col) {
+    const long n = (long)d_row * d_col;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int j = (int)(i % d_col);
+        if (H[(size_t)j * d_col + j] == 0.0f) W[i] = 0.0f;
+    }
+}
+__global__ void fix_dead_diag_kernel(float *H, int d_col) {   // gptq.py:135
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < d_col && H[(size_t)j * d_col + j] == 0.0f) H[(size_t)j * d_col + j] = 1.0f;
+}
+
+// nz[j] |= any(W[:, j] != 0)   (gptq.py:308)
+__global__ void col_nonzero_kernel(const float *__restrict__ W, int d_row, int d_col, int rows_per_block, int *nz) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d_col) return;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(d_row, r0 + rows_per_block);
+    int any = 0;
+    for (int r = r0; r < r1; ++r) any |= (W[(size_t)r * d_col + j] != 0.0f);
+    if (any) nz[j] = 1;
+}
+// H[z,:] = 0, H[:,z] = 0, H[z,z] = 1 for all-zero weight columns z (gptq.py:311-313)
+__global__ void mask_zero_cols_kernel(float *H, int n, const int *__restrict__ nz) {
+    const long total = (long)n * n;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / n), c = (int)(i % n);
+        if (!nz[r] || !nz[c]) H[i] = (r == c) ? 1.0f : 0.0f;
+    }
+}
+// H[i,i] += rel_damp * mean(diag H)  (gptq.py:315-316); one CTA, fixed summation order, double accumulator.
+__global__ void __launch_bounds__(1024) damp_kernel(float *H, int n, float rel_damp) {
+    __shared__ double part[1024];
+    __shared__ float damp_s;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) s += (double)H[(size_t)i * n + i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) damp_s = __fmul_rn(rel_damp, (float)(part[0] / (double)n));
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 1024) H[(size_t)i * n + i] = __fadd_rn(H[(size_t)i * n + i], damp_s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cholesky chain
+// ---------------------------------------------------------------------------------------------
+// A[i][j] = H[n-1-i][n-1-j]   (lower triangle is what the factorisation reads)
+__global__ void reverse_copy_kernel(const float *__restrict__ H, float *A, int n) {
+    const long total = (long)n * n;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x)
+        A[i] = H[total - 1 - i];
+}
+
+// Factor the (128 x 128) diagonal block at A[k0:k0+128, k0:k0+128] in shared memory: L_kk (written back to A)
+// and inv(L_kk) (written to Binv, the level-0 blocks of the triangular inverse; upper part zeroed).
+constexpr int DT = 512;
+struct DiagSmem { float L[NB][NB + 1]; float X[NB][NB + 1]; };
+__global__ void __launch_bounds__(DT) chol_diag_kernel(float *A, float *Binv, long ld, int k0, int *not_pd) {
+    extern __shared__ __align__(16) uint8_t raw[];
+    DiagSmem &s = *reinterpret_cast<DiagSmem *>(raw);
+    const int tid = threadIdx.x;
+    float *Ab = A + (size_t)k0 * ld + k0;
+    float *Bb = Binv + (size_t)k0 * ld + k0;
+    for (int id = tid; id < NB * NB; id += DT) {
+        const int i = id >> 7, j = id & 127;
+        s.L[i][j] = (j <= i) ? Ab[(size_t)i * ld + j] : 0.0f;
+    }
+    __syncthreads();
+    for (int j = 0; j < NB; ++j) {
+        if (tid == 0) {
+            float piv = s.L[j][j];
+            if (!(piv > 0.0f) || !isfinite(piv)) { *not_pd = 1; piv = 1.0f; }
+            s.L[j][j] = __fsqrt_rn(piv);
+        }
+        __syncthreads();
+        const float inv = __frcp_rn(s.L[j][j]);
+        for (int i = j + 1 + tid; i < NB; i += DT) s.L[i][j] = __fmul_rn(s.L[i][j], inv);
+        __syncthreads();
+        const int m = NB - 1 - j;   // trailing size
+        for (int id = tid; id < m * m; id += DT) {
+            const int i = j + 1 + id / m, k = j + 1 + id % m;
+            if (k <= i) s.L[i][k] = __fmaf_rn(-s.L[i][j], s.L[k][j], s.L[i][k]);
+        }
+        __syncthreads();
+    }
+    // X = inv(L): thread c owns column c, forward substitution in lock step over (i, k)
+    if (tid < NB) {
+        const int c = tid;
+        for (int i = 0; i < NB; ++i) {
+            float acc = (i == c) ? 1.0f : 0.0f;
+            for (int k = 0; k < i; ++k) {
+                const float xk = (k >= c) ? s.X[k][c] : 0.0f;
+                acc = __fmaf_rn(-s.L[i][k], xk, acc);
+            }
+            s.X[i][c] = (i >= c) ? __fdiv_rn(acc, s.L[i][i]) : 0.0f;
+        }
+    }
+    __syncthreads();
+    for (int id = tid; id < NB * NB; id += DT) {
+        const int i = id >> 7, j = id & 127;
+        if (j <= i) Ab[(size_t)i * ld + j] = s.L[i][j];
+        Bb[(size_t)i * ld + j] = s.X[i][j];
+    }
+}
+
+// U[i][j] = Linv[n-1-i][n-1-j] for j >= i, 0 below; identity if the factorisation failed (gptq.py:321-323).
+__global__ void finish_u_kernel(const float *__restrict__ Linv, float *U, int n, const int *__restrict__ not_pd) {
+    const long total = (long)n * n;
+    const int bad = *not_pd;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / n), j = (int)(idx % n);
+        float v;
+        if (bad) v = (i == j) ? 1.0f : 0.0f;
+        else v = (j >= i) ? Linv[total - 1 - idx] : 0.0f;
+        U[idx] = v;
+    }
+}
+__global__ void copy_flag_kernel(const int *src, int *dst) { *dst = *src; }
+
+int ew_grid(long n) {
+    long g = (n + 255) / 256;
+    const long cap = 148L * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+sg::Args gemm_args(const float *A, long a_rs, long a_cs, const float *B, long b_rs, long b_cs, float *C, long ldc,
+                   int M, int N, int K, float alpha, float beta, int tile_mode, int k_mode) {
+    sg::Args a;
+    a.A = A; a.B = B; a.C = C; a.a_rs = a_rs; a.a_cs = a_cs; a.b_rs = b_rs; a.b_cs = b_cs; a.ldc = ldc;
+    a.a_batch = a.b_batch = a.c_batch = 0;
+    a.M = M; a.N = N; a.K = K; a.alpha = alpha; a.beta = beta; a.tile_mode = tile_mode; a.k_mode = k_mode;
+    a.in_dtype = GQ_F32;
+    return a;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" size_t gq_hessian_workspace_bytes(long n_tok, int d_col, int x_dtype) {
+    (void)n_tok; (void)d_col; (void)x_dtype;
+    return 0;
+}
+
+extern "C" int gq_hessian_update(float *H, const void *X, long n_tok, int d_col, int x_dtype, float beta, float alpha,
+                                 void *workspace, size_t ws_bytes, gq_stream_t stream) {
+    (void)workspace; (void)ws_bytes;
+    GQ_REQUIRE(H && X, "gq_hessian_update: null pointer");
+    GQ_REQUIRE(d_col > 0 && d_col % 128 == 0, "gq_hessian_update: d_col=%d must be a positive multiple of 128", d_col);
+    GQ_REQUIRE(n_tok > 0 && n_tok < (1L << 31), "gq_hessian_update: bad n_tok %ld", n_tok);
+    GQ_REQUIRE(x_dtype >= GQ_F32 && x_dtype <= GQ_BF16, "gq_hessian_update: bad x_dtype %d", x_dtype);
+    sg::Args a;
+    a.A = X; a.B = X; a.C = H;
+    a.a_rs = 1; a.a_cs = d_col;      // A(m,k) = X[k][m]
+    a.b_rs = d_col; a.b_cs = 1;      // B(k,n) = X[k][n]
+    a.ldc = d_col; a.a_batch = a.b_batch = a.c_batch = 0;
+    a.M = d_col; a.N = d_col; a.K = (int)n_tok;
+    a.alpha = alpha; a.beta = beta; a.tile_mode = sg::TM_UPPER_MIRROR; a.k_mode = sg::KM_FULL; a.in_dtype = x_dtype;
+    return sg::launch(a, 1, (cudaStream_t)stream);
+}
+
+extern "C" int gq_pre_step(float *H, float *W, int d_row, int d_col, gq_stream_t stream) {
+    GQ_REQUIRE(H && W && d_row > 0 && d_col > 0, "gq_pre_step: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    zero_dead_cols_kernel<<<ew_grid((long)d_row * d_col), 256, 0, st>>>(H, W, d_row, d_col);
+    fix_dead_diag_kernel<<<(d_col + 255) / 256, 256, 0, st>>>(H, d_col);
+    GQ_CHECK_CUDA(cudaGetLastError());
+    return GQ_OK;
+}
+
+// workspace: A (n*n) | Linv (n*n) | nz (n ints) | flag (1 int, padded)
+extern "C" size_t gq_prepare_workspace_bytes(int d_col) {
+    const size_t n = (size_t)d_col;
+    return 2 * n * n * sizeof(float) + (n + 64) * sizeof(int);
+}
+
+extern "C" int gq_prepare(float *H, const float *W, int d_row, int d_col, float rel_damp, float *U_out, void *workspace,
+                          size_t ws_bytes, int *not_pd_flag, gq_stream_t stream) {
+    GQ_REQUIRE(H && W && U_out && workspace, "gq_prepare: null pointer");
+    GQ_REQUIRE(d_row > 0 && d_col > 0 && d_col % NB == 0, "gq_prepare: d_col=%d must be a positive multiple of 128", d_col);
+    if (ws_bytes < gq_prepare_workspace_bytes(d_col)) {
+        gq_set_error("gq_prepare: workspace %zu < %zu bytes", ws_bytes, gq_prepare_workspace_bytes(d_col));
+        return GQ_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = d_col;
+    const long ld = n;
+    float *A = (float *)workspace;
+    float *Li = A + (size_t)n * n;
+    int *nz = (int *)(Li + (size_t)n * n);
+    int *flag = nz + n;
+
+    // --- masks + damping (gptq.py:308-316) ---
+    GQ_CHECK_CUDA(cudaMemsetAsync(nz, 0, (size_t)(n + 64) * sizeof(int), st));
+    {
+        const int rpb = 256;
+        dim3 g((n + 255) / 256, (d_row + rpb - 1) / rpb);
+        col_nonzero_kernel<<<g, 256, 0, st>>>(W, d_row, n, rpb, nz);
+    }
+    mask_zero_cols_kernel<<<ew_grid((long)n * n), 256, 0, st>>>(H, n, nz);
+    damp_kernel<<<1, 1024, 0, st>>>(H, n, rel_damp);
+
+    // --- L = chol(J H J), level-0 blocks of inv(L) ---
+    reverse_copy_kernel<<<ew_grid((long)n * n), 256, 0, st>>>(H, A, n);
+    GQ_CHECK_CUDA(cudaMemsetAsync(Li, 0, (size_t)n * n * sizeof(float), st));
+    GQ_CHECK_CUDA(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DiagSmem)));
+    for (int k0 = 0; k0 < n; k0 += NB) {
+        chol_diag_kernel<<<1, DT, sizeof(DiagSmem), st>>>(A, Li, ld, k0, flag);
+        const int rem = n - k0 - NB;
+        if (rem > 0) {
+            float *P = A + (size_t)(k0 + NB) * ld + k0;          // panel (rem x 128)
+            const float *Lkk_inv = Li + (size_t)k0 * ld + k0;     // inv(L_kk)
+            // P <- P * inv(L_kk)^T   : A(m,k) = P[m][k], B(k,n) = Lkk_inv[n][k]; B lower-tri => k <= n, one tile: full
+            int rc = sg::launch(gemm_args(P, ld, 1, Lkk_inv, 1, ld, P, ld, rem, NB, NB, 1.0f, 0.0f, sg::TM_FULL, sg::KM_FULL), 1, st);
+            if (rc) return rc;
+            // trailing lower triangle:  T <- T - P P^T
+            float *T = A + (size_t)(k0 + NB) * ld + (k0 + NB);
+            rc = sg::launch(gemm_args(P, ld, 1, P, 1, ld, T, ld, rem, rem, NB, -1.0f, 1.0f, sg::TM_LOWER, sg::KM_FULL), 1, st);
+            if (rc) return rc;
+        }
+    }
+
+    // --- inv(L) by pairwise merging of diagonal blocks; U_out is the scratch for C * Ai ---
+    // blocks are described by their boundaries; every level merges neighbours (sizes may differ at the tail)
+    {
+        int nblk = n / NB;
+        int *start = new int[nblk + 1];
+        for (int i = 0; i <= nblk; ++i) start[i] = i * NB;
+        while (nblk > 1) {
+            int out = 0;
+            for (int b = 0; b + 1 < nblk; b += 2) {
+                const int r1 = start[b], r2 = start[b + 1], r3 = start[b + 2];
+                const int s1 = r2 - r1, s2 = r3 - r2;
+                const float *C = A + (size_t)r2 * ld + r1;      // L[rows2, cols1]   (s2 x s1)
+                const float *Ai = Li + (size_t)r1 * ld + r1;    // inv block 1       (s1 x s1, lower)
+                const float *Bi = Li + (size_t)r2 * ld + r2;    // inv block 2       (s2 x s2, lower)
+                float *Tm = U_out + (size_t)r2 * ld + r1;       // scratch           (s2 x s1)
+                float *O = Li + (size_t)r2 * ld + r1;           // result            (s2 x s1)
+                int rc = sg::launch(gemm_args(C, ld, 1, Ai, ld, 1, Tm, ld, s2, s1, s1, 1.0f, 0.0f, sg::TM_FULL, sg::KM_FROM_N), 1, st);
+                if (rc) { delete[] start; return rc; }
+                rc = sg::launch(gemm_args(Bi, ld, 1, Tm, ld, 1, O, ld, s2, s1, s2, -1.0f, 0.0f, sg::TM_FULL, sg::KM_TO_M), 1, st);
+                if (rc) { delete[] start; return rc; }
+                start[out++] = r1;
+            }
+            if (nblk & 1) start[out++] = start[nblk - 1];
+            start[out] = n;
+            nblk = out;
+        }
+        delete[] start;
+    }
+
+    finish_u_kernel<<<ew_grid((long)n * n), 256, 0, st>>>(Li, U_out, n, flag);
+    if (not_pd_flag) copy_flag_kernel<<<1, 1, 0, st>>>(flag, not_pd_flag);
+    GQ_CHECK_CUDA(cudaGetLastError());
+    return GQ_OK;
+}

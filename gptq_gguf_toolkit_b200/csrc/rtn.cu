@@ -1,0 +1,240 @@
+// rtn.cu -- Hessian-free K-quant kernels:
+//   gq_rtn_quantize        (replaces Quantizer._quant_non_block_module, quant/gptq/src/quantizer.py:278-330)
+//   gq_get_scale_and_zero  (replaces quant_utils.Quantizer.get_scale_and_zero, quant_utils.py:90-145)
+//   gq_dequantize          (replaces dequantize_linear_weight, quant_utils.py:277-310)
+//   gq_pack                (replaces pack_Q2K..pack_Q6K, packing_utils.py:33-326)
+// One CTA handles a (32 rows x 256 columns) super-block tile; the grid covers (row tiles, super-blocks), so
+// embed_tokens / lm_head (128256 x 4096) launch 4008 x 16 independent CTAs -- purely HBM/ALU work, no GEMM.
+#include "tile.cuh"
+
+namespace {
+
+constexpr int R = 32;
+constexpr int NT = 256;
+
+struct RtnParams {
+    const void *W;       // (d_row, *) of w_dtype, row stride ld_in elements
+    int w_dtype;
+    long ld_in;
+    int d_row, nsb;
+    SearchParams sp;
+    // metadata outputs: d/dmin at [row*d_stride + sb], sq/zq at [row*sq_stride + sb*GPR + g]
+    uint16_t *d, *dmin;
+    long d_stride;
+    uint8_t *sq, *zq;
+    long sq_stride;
+    // optional full-matrix outputs (row stride = nsb*256 elements)
+    uint8_t *qweight;
+    uint8_t *packed;
+    void *wdeq;
+    int wdeq_dtype;
+    uint32_t *flags;
+};
+
+struct __align__(16) RtnSmem {
+    float Wt[R * 256];
+    uint8_t codes[R * 256];
+    float gsc[R * 16];
+    float gzr[R * 16];
+    RowScales<R> rs;
+};
+
+template <int QT>
+__global__ void __launch_bounds__(NT) rtn_kernel(const RtnParams p) {
+    __shared__ RtnSmem sm;
+    constexpr int GS = Fmt<QT>::GS, GPR = GQ_QK_K / GS;
+    const int tid = threadIdx.x;
+    const int r0 = blockIdx.x * R, sb = blockIdx.y, c = sb * GQ_QK_K;
+
+    for (int id = tid; id < R * 64; id += NT) {
+        const int row = id >> 6, c4 = id & 63;
+        const long base = (long)min(r0 + row, p.d_row - 1) * p.ld_in + c + 4 * c4;
+        float4 v;
+        if (p.w_dtype == GQ_F32) {
+            v = *reinterpret_cast<const float4 *>((const float *)p.W + base);
+        } else {
+            v.x = load_as_f32(p.W, base + 0, p.w_dtype); v.y = load_as_f32(p.W, base + 1, p.w_dtype);
+            v.z = load_as_f32(p.W, base + 2, p.w_dtype); v.w = load_as_f32(p.W, base + 3, p.w_dtype);
+        }
+        *reinterpret_cast<float4 *>(sm.Wt + wt_idx4(row, c4)) = v;
+    }
+    __syncthreads();
+    uint32_t vmask = 0, amask = 0;
+    tile_search<QT, R, NT>(sm.Wt, sm.gsc, sm.gzr, p.sp, vmask, amask);
+    publish_flags(p.flags ? p.flags + 2 * sb : nullptr, vmask, amask);
+    __syncthreads();
+    if (tid < R) {
+        tile_finalize_row<QT, R>(tid, sm.gsc, sm.gzr, sm.rs);
+        if (r0 + tid < p.d_row) {
+            const long gr = r0 + tid;
+            p.d[gr * p.d_stride + sb] = sm.rs.dbits[tid];
+            p.dmin[gr * p.d_stride + sb] = sm.rs.dmbits[tid];
+#pragma unroll
+            for (int g = 0; g < GPR; ++g) {
+                p.sq[gr * p.sq_stride + sb * GPR + g] = sm.rs.sq[tid][g];
+                p.zq[gr * p.sq_stride + sb * GPR + g] = sm.rs.zq[tid][g];
+            }
+        }
+    }
+    if (p.qweight == nullptr && p.packed == nullptr && p.wdeq == nullptr) return;
+    __syncthreads();
+    // quantize every weight of the tile (quantizer.py:323 -> quant_utils.py:34-40)
+    const float lo = (float)Fmt<QT>::QMIN, hi = (float)Fmt<QT>::QMAX;
+    for (int id = tid; id < R * 256; id += NT) {
+        const int row = id >> 8, col = id & 255, g = col / GS;
+        const float s = __fmul_rn(sm.rs.d[row], kq_code_to_f<QT>(sm.rs.sq[row][g]));
+        const float z = __fmul_rn(sm.rs.dm[row], kq_code_to_f<QT>(sm.rs.zq[row][g]));
+        const int wi = wt_idx(row, col);
+        const float q = kq_quant(sm.Wt[wi], s, z, lo, hi);
+        sm.codes[row * 256 + col] = (uint8_t)(int8_t)(int)q;
+        sm.Wt[wi] = kq_dequant(q, s, z);
+    }
+    __syncthreads();
+    tile_emit<QT, R, NT>(sm.Wt, sm.codes, sm.rs, r0, p.d_row, (size_t)p.nsb * GQ_QK_K, c, sb, p.nsb, p.qweight,
+                         p.packed, p.wdeq, p.wdeq_dtype);
+}
+
+template <int QT> int launch_rtn(const RtnParams &p, cudaStream_t st) {
+    dim3 grid((p.d_row + R - 1) / R, p.nsb);
+    rtn_kernel<QT><<<grid, NT, 0, st>>>(p);
+    GQ_CHECK_CUDA(cudaGetLastError());
+    return GQ_OK;
+}
+
+int dispatch_rtn(int qtype, const RtnParams &p, cudaStream_t st) {
+    switch (qtype) {
+    case GQ_Q2_K: return launch_rtn<GQ_Q2_K>(p, st);
+    case GQ_Q3_K: return launch_rtn<GQ_Q3_K>(p, st);
+    case GQ_Q4_K: return launch_rtn<GQ_Q4_K>(p, st);
+    case GQ_Q5_K: return launch_rtn<GQ_Q5_K>(p, st);
+    default: return launch_rtn<GQ_Q6_K>(p, st);
+    }
+}
+
+// ---- dequantize_linear_weight ----------------------------------------------------------------
+template <int QT>
+__global__ void dequant_kernel(const uint8_t *__restrict__ qw, const uint16_t *__restrict__ d,
+                               const uint8_t *__restrict__ sq, const uint16_t *__restrict__ dmin,
+                               const uint8_t *__restrict__ zq, int d_row, int d_col, void *out, int out_dtype) {
+    constexpr int GS = Fmt<QT>::GS;
+    const long n4 = (long)d_row * d_col / 4;
+    const int nsb = d_col / GQ_QK_K, ng = d_col / GS;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        const long e = i * 4;
+        const long row = e / d_col;
+        const int col = (int)(e % d_col);
+        const float s = __fmul_rn(__half2float(__ushort_as_half(d[row * nsb + col / GQ_QK_K])),
+                                  kq_code_to_f<QT>(sq[row * ng + col / GS]));
+        const float z = __fmul_rn(__half2float(__ushort_as_half(dmin[row * nsb + col / GQ_QK_K])),
+                                  kq_code_to_f<QT>(zq[row * ng + col / GS]));
+        const uchar4 c4 = *reinterpret_cast<const uchar4 *>(qw + e);
+        const float v0 = kq_dequant(kq_code_to_f<QT>(c4.x), s, z), v1 = kq_dequant(kq_code_to_f<QT>(c4.y), s, z);
+        const float v2 = kq_dequant(kq_code_to_f<QT>(c4.z), s, z), v3 = kq_dequant(kq_code_to_f<QT>(c4.w), s, z);
+        store_from_f32(out, e + 0, out_dtype, v0); store_from_f32(out, e + 1, out_dtype, v1);
+        store_from_f32(out, e + 2, out_dtype, v2); store_from_f32(out, e + 3, out_dtype, v3);
+    }
+}
+
+// ---- pack_Q*K --------------------------------------------------------------------------------
+template <int QT>
+__global__ void pack_kernel(const uint8_t *__restrict__ qw, const uint16_t *__restrict__ d,
+                            const uint8_t *__restrict__ sq, const uint16_t *__restrict__ dmin,
+                            const uint8_t *__restrict__ zq, long nblk, uint8_t *out) {
+    constexpr int TS = Fmt<QT>::TS, GPR = GQ_QK_K / Fmt<QT>::GS;
+    const long total = nblk * TS;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long blk = i / TS;
+        const int b = (int)(i % TS);
+        // Q3_K / Q6_K blocks carry no min: dmin / zq may be NULL for them (pack_Q3K / pack_Q6K take 3 tensors)
+        out[i] = kq_pack_byte<QT>(b, qw + blk * GQ_QK_K, sq + blk * GPR, zq ? zq + blk * GPR : nullptr, d[blk],
+                                  dmin ? dmin[blk] : (uint16_t)0);
+    }
+}
+
+int grid_for(long n, int bs) {
+    long g = (n + bs - 1) / bs;
+    const long cap = 148L * 32;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+void gq_fill_search_params(SearchParams &sp, int maxq, double rmin, double rdelta, int nstep);
+
+extern "C" int gq_rtn_quantize(const void *W, int w_dtype, int d_row, int d_col, int qtype, double rmin,
+                               double rdelta, int nstep, void *qweight, uint16_t *d, void *sq, uint16_t *dmin,
+                               void *zq, uint8_t *packed, void *wdeq, int wdeq_dtype, gq_stream_t stream) {
+    FmtInfo f;
+    GQ_REQUIRE(gq_fmt_info(qtype, f), "gq_rtn_quantize: unknown q_type %d", qtype);
+    GQ_REQUIRE(W && qweight && d && sq && dmin && zq, "gq_rtn_quantize: null pointer");
+    GQ_REQUIRE(d_row > 0 && d_col > 0 && d_col % GQ_QK_K == 0, "gq_rtn_quantize: d_col=%d must be a positive multiple of 256", d_col);
+    GQ_REQUIRE(w_dtype >= GQ_F32 && w_dtype <= GQ_BF16, "gq_rtn_quantize: bad w_dtype %d", w_dtype);
+    GQ_REQUIRE(nstep >= 0 && nstep < 64, "gq_rtn_quantize: nstep=%d out of range [0,63]", nstep);
+    GQ_REQUIRE(((uintptr_t)W | (uintptr_t)qweight | (uintptr_t)wdeq) % 16 == 0, "gq_rtn_quantize: W, qweight, wdeq must be 16-byte aligned");
+    RtnParams p;
+    p.W = W; p.w_dtype = w_dtype; p.ld_in = d_col; p.d_row = d_row; p.nsb = d_col / GQ_QK_K;
+    gq_fill_search_params(p.sp, (1 << f.bits) - 1, rmin, rdelta, nstep);
+    p.d = d; p.dmin = dmin; p.d_stride = p.nsb; p.sq = (uint8_t *)sq; p.zq = (uint8_t *)zq; p.sq_stride = d_col / f.gs;
+    p.qweight = (uint8_t *)qweight; p.packed = packed; p.wdeq = wdeq; p.wdeq_dtype = wdeq_dtype; p.flags = nullptr;
+    return dispatch_rtn(qtype, p, (cudaStream_t)stream);
+}
+
+extern "C" int gq_get_scale_and_zero(const float *x, long x_stride, int rows, int qtype, double rmin, double rdelta,
+                                     int nstep, uint16_t *d, uint16_t *dmin, long d_stride, void *sq, void *zq,
+                                     long sq_stride, uint32_t *search_flags, gq_stream_t stream) {
+    FmtInfo f;
+    GQ_REQUIRE(gq_fmt_info(qtype, f), "gq_get_scale_and_zero: unknown q_type %d", qtype);
+    GQ_REQUIRE(x && d && dmin && sq && zq, "gq_get_scale_and_zero: null pointer");
+    GQ_REQUIRE(rows > 0 && x_stride >= GQ_QK_K && x_stride % 4 == 0 && (uintptr_t)x % 16 == 0,
+               "gq_get_scale_and_zero: x must be 16-byte aligned with a row stride that is a multiple of 4");
+    GQ_REQUIRE(nstep >= 0 && nstep < 64, "gq_get_scale_and_zero: nstep=%d out of range [0,63]", nstep);
+    RtnParams p;
+    p.W = x; p.w_dtype = GQ_F32; p.ld_in = x_stride; p.d_row = rows; p.nsb = 1;
+    gq_fill_search_params(p.sp, (1 << f.bits) - 1, rmin, rdelta, nstep);
+    p.d = d; p.dmin = dmin; p.d_stride = d_stride; p.sq = (uint8_t *)sq; p.zq = (uint8_t *)zq; p.sq_stride = sq_stride;
+    p.qweight = nullptr; p.packed = nullptr; p.wdeq = nullptr; p.wdeq_dtype = GQ_F32; p.flags = search_flags;
+    return dispatch_rtn(qtype, p, (cudaStream_t)stream);
+}
+
+extern "C" int gq_dequantize(int qtype, const void *qweight, const uint16_t *d, const void *sq, const uint16_t *dmin,
+                             const void *zq, int d_row, int d_col, void *out, int out_dtype, gq_stream_t stream) {
+    FmtInfo f;
+    GQ_REQUIRE(gq_fmt_info(qtype, f), "gq_dequantize: unknown q_type %d", qtype);
+    GQ_REQUIRE(qweight && d && sq && dmin && zq && out, "gq_dequantize: null pointer");
+    GQ_REQUIRE(d_row > 0 && d_col > 0 && d_col % GQ_QK_K == 0, "gq_dequantize: d_col=%d must be a positive multiple of 256", d_col);
+    GQ_REQUIRE(out_dtype >= GQ_F32 && out_dtype <= GQ_BF16, "gq_dequantize: bad out_dtype %d", out_dtype);
+    GQ_REQUIRE((uintptr_t)qweight % 4 == 0, "gq_dequantize: qweight must be 4-byte aligned");
+    const int g = grid_for((long)d_row * d_col / 4, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint8_t *q = (const uint8_t *)qweight, *s = (const uint8_t *)sq, *z = (const uint8_t *)zq;
+    switch (qtype) {
+    case GQ_Q2_K: dequant_kernel<GQ_Q2_K><<<g, 256, 0, st>>>(q, d, s, dmin, z, d_row, d_col, out, out_dtype); break;
+    case GQ_Q3_K: dequant_kernel<GQ_Q3_K><<<g, 256, 0, st>>>(q, d, s, dmin, z, d_row, d_col, out, out_dtype); break;
+    case GQ_Q4_K: dequant_kernel<GQ_Q4_K><<<g, 256, 0, st>>>(q, d, s, dmin, z, d_row, d_col, out, out_dtype); break;
+    case GQ_Q5_K: dequant_kernel<GQ_Q5_K><<<g, 256, 0, st>>>(q, d, s, dmin, z, d_row, d_col, out, out_dtype); break;
+    default: dequant_kernel<GQ_Q6_K><<<g, 256, 0, st>>>(q, d, s, dmin, z, d_row, d_col, out, out_dtype); break;
+    }
+    GQ_CHECK_CUDA(cudaGetLastError());
+    return GQ_OK;
+}
+
+extern "C" int gq_pack(int qtype, const void *qweight, const uint16_t *d, const void *sq, const uint16_t *dmin,
+                       const void *zq, int d_row, int d_col, uint8_t *out, gq_stream_t stream) {
+    FmtInfo f;
+    GQ_REQUIRE(gq_fmt_info(qtype, f), "gq_pack: unknown q_type %d", qtype);
+    GQ_REQUIRE(qweight && d && sq && out && (f.asym == 0 || (dmin && zq)), "gq_pack: null pointer");
+    GQ_REQUIRE(d_row > 0 && d_col > 0 && d_col % GQ_QK_K == 0, "gq_pack: d_col=%d must be a positive multiple of 256", d_col);
+    const long nblk = (long)d_row * (d_col / GQ_QK_K);
+    const int g = grid_for(nblk * f.ts, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint8_t *q = (const uint8_t *)qweight, *s = (const uint8_t *)sq, *z = (const uint8_t *)zq;
+    switch (qtype) {
+    case GQ_Q2_K: pack_kernel<GQ_Q2_K><<<g, 256, 0, st>>>(q, d, s, dmin, z, nblk, out); break;
+    case GQ_Q3_K: pack_kernel<GQ_Q3_K><<<g, 256, 0, st>>>(q, d, s, dmin, z, nblk, out); break;
+    case GQ_Q4_K: pack_kernel<GQ_Q4_K><<<g, 256, 0, st>>>(q, d, s, dmin, z, nblk, out); break;
+    case GQ_Q5_K: pack_kernel<GQ_Q5_K><<<g, 256, 0, st>>>(q, d, s, dmin, z, nblk, out); break;
+    default: pack_kernel<GQ_Q6_K><<<g, 256, 0, st>>>(q, d, s, dmin, z, nblk, out); break;
+    }
+    GQ_CHECK_CUDA(cudaGetLastError());
+    return GQ_OK;
+}

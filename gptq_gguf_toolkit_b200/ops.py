@@ -1,0 +1,159 @@
+"""Torch-tensor front-end of the C ABI (include/gq.h): allocation and argument marshalling only.
+
+Every function enqueues on torch's current stream of the tensors' device and returns immediately; the
+five K-quant tensors are always returned in the reference's order
+    (qweight, super_group_scale, group_scale_quant, super_group_zero, group_zero_quant)
+(quant/gptq/src/gptq.py:295 of the reference).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+QK_K = 256
+_ws_cache: dict = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    """One growing scratch buffer per device (torch caching allocator owns the memory)."""
+    key = (device.type, device.index)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        _ws_cache[key] = ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+    return ws
+
+
+def release_workspaces():
+    _ws_cache.clear()
+
+
+def _code_dtype(fmt) -> torch.dtype:
+    return torch.uint8 if fmt["asym"] else torch.int8
+
+
+def alloc_outputs(q_type: int, d_row: int, d_col: int, device, packed: bool, wdeq_dtype: Optional[torch.dtype]):
+    f = L.format_info(q_type)
+    cd = _code_dtype(f)
+    nsb, ng = d_col // QK_K, d_col // f["group_size"]
+    qweight = torch.empty(d_row, d_col, dtype=cd, device=device)
+    d = torch.empty(d_row, nsb, dtype=torch.float16, device=device)
+    dmin = torch.empty(d_row, nsb, dtype=torch.float16, device=device)
+    sq = torch.empty(d_row, ng, dtype=cd, device=device)
+    zq = torch.empty(d_row, ng, dtype=cd, device=device)
+    pk = torch.empty(d_row, nsb * f["type_size"], dtype=torch.uint8, device=device) if packed else None
+    wd = torch.empty(d_row, d_col, dtype=wdeq_dtype, device=device) if wdeq_dtype is not None else None
+    return qweight, d, sq, dmin, zq, pk, wd
+
+
+def hessian_update(H: torch.Tensor, X: torch.Tensor, beta: float, alpha: float) -> None:
+    """H <- beta*H + alpha*X^T X  (gptq.py:110-112).  X: (n_tok, d_col) contiguous, fp32/fp16/bf16."""
+    L.require_cuda(H, X)
+    assert H.dtype == torch.float32 and H.is_contiguous() and X.is_contiguous() and X.dim() == 2
+    n_tok, d_col = X.shape
+    lib = L.load()
+    code = L.dtype_code(X.dtype)
+    nws = lib.gq_hessian_workspace_bytes(n_tok, d_col, code)
+    ws = _workspace(H.device, nws) if nws else None
+    L.check(lib.gq_hessian_update(L.ptr(H), L.ptr(X), n_tok, d_col, code, float(beta), float(alpha),
+                                  L.ptr(ws), nws, L.stream_of(H.device)))
+
+
+def pre_step(H: torch.Tensor, W: torch.Tensor) -> None:
+    """Dead-channel fix (gptq.py:134-141), in place on H and the fp32 working copy W."""
+    L.require_cuda(H, W)
+    assert W.dtype == torch.float32 and W.is_contiguous() and H.is_contiguous()
+    L.check(L.load().gq_pre_step(L.ptr(H), L.ptr(W), W.shape[0], W.shape[1], L.stream_of(H.device)))
+
+
+def prepare(H: torch.Tensor, W: torch.Tensor, rel_damp: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """U = chol(inv(H + damp I), upper), row-major (gptq.py:305-324).  H is masked + damped in place.
+    Returns (U, not_pd) where not_pd is a device int32 scalar (1 => U is the identity)."""
+    L.require_cuda(H, W)
+    assert H.dtype == torch.float32 and H.is_contiguous() and W.dtype == torch.float32 and W.is_contiguous()
+    d_row, d_col = W.shape
+    lib = L.load()
+    U = torch.empty(d_col, d_col, dtype=torch.float32, device=H.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=H.device)
+    nws = lib.gq_prepare_workspace_bytes(d_col)
+    ws = _workspace(H.device, nws)
+    L.check(lib.gq_prepare(L.ptr(H), L.ptr(W), d_row, d_col, float(rel_damp), L.ptr(U), L.ptr(ws), nws,
+                           L.ptr(flag), L.stream_of(H.device)))
+    return U, flag
+
+
+def gptq_quantize(W: torch.Tensor, U: torch.Tensor, q_type: int, block_size: int = 128, rmin: float = -1.0,
+                  rdelta: float = 0.1, nstep: int = 20, mode: int = L.GQ_MODE_EXACT, packed: bool = True,
+                  wdeq_dtype: Optional[torch.dtype] = None, search_flags: bool = False):
+    """The column loop of one layer (gptq.py:146-295).  W: fp32 working copy, CLOBBERED.
+    Returns (qweight, d, sq, dmin, zq, packed|None, wdeq|None, flags|None)."""
+    L.require_cuda(W, U)
+    assert W.dtype == torch.float32 and W.is_contiguous() and U.dtype == torch.float32 and U.is_contiguous()
+    d_row, d_col = W.shape
+    qweight, d, sq, dmin, zq, pk, wd = alloc_outputs(q_type, d_row, d_col, W.device, packed, wdeq_dtype)
+    flags = torch.zeros(d_col // QK_K, 2, dtype=torch.int32, device=W.device) if search_flags else None
+    L.check(L.load().gq_gptq_quantize(
+        L.ptr(W), L.ptr(U), d_row, d_col, int(q_type), int(block_size), float(rmin), float(rdelta), int(nstep), int(mode),
+        L.ptr(qweight), L.ptr(d), L.ptr(sq), L.ptr(dmin), L.ptr(zq), L.ptr(pk), L.ptr(wd),
+        L.dtype_code(wdeq_dtype) if wdeq_dtype is not None else 0, L.ptr(flags), L.stream_of(W.device)))
+    return qweight, d, sq, dmin, zq, pk, wd, flags
+
+
+def rtn_quantize(W: torch.Tensor, q_type: int, rmin: float = -1.0, rdelta: float = 0.1, nstep: int = 20,
+                 packed: bool = True, wdeq_dtype: Optional[torch.dtype] = None):
+    """RTN K-quant of a weight without Hessian (quantizer.py:278-330).  W is read-only (fp32/fp16/bf16).
+    Returns (qweight, d, sq, dmin, zq, packed|None, wdeq|None)."""
+    L.require_cuda(W)
+    assert W.is_contiguous() and W.dim() == 2
+    d_row, d_col = W.shape
+    qweight, d, sq, dmin, zq, pk, wd = alloc_outputs(q_type, d_row, d_col, W.device, packed, wdeq_dtype)
+    L.check(L.load().gq_rtn_quantize(
+        L.ptr(W), L.dtype_code(W.dtype), d_row, d_col, int(q_type), float(rmin), float(rdelta), int(nstep),
+        L.ptr(qweight), L.ptr(d), L.ptr(sq), L.ptr(dmin), L.ptr(zq), L.ptr(pk), L.ptr(wd),
+        L.dtype_code(wdeq_dtype) if wdeq_dtype is not None else 0, L.stream_of(W.device)))
+    return qweight, d, sq, dmin, zq, pk, wd
+
+
+def get_scale_and_zero(x: torch.Tensor, q_type: int, rmin: float = -1.0, rdelta: float = 0.1, nstep: int = 20):
+    """quant_utils.py:90-145.  x: (rows, 256) fp32 (row stride may exceed 256).
+    Returns (super_group_scale, group_scale_quant, super_group_zero, group_zero_quant)."""
+    L.require_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] == QK_K and x.stride(1) == 1
+    rows = x.shape[0]
+    f = L.format_info(q_type)
+    gpr = QK_K // f["group_size"]
+    cd = _code_dtype(f)
+    d = torch.empty(rows, dtype=torch.float16, device=x.device)
+    dmin = torch.empty(rows, dtype=torch.float16, device=x.device)
+    sq = torch.empty(rows, gpr, dtype=cd, device=x.device)
+    zq = torch.empty(rows, gpr, dtype=cd, device=x.device)
+    L.check(L.load().gq_get_scale_and_zero(
+        L.ptr(x), x.stride(0), rows, int(q_type), float(rmin), float(rdelta), int(nstep),
+        L.ptr(d), L.ptr(dmin), 1, L.ptr(sq), L.ptr(zq), gpr, None, L.stream_of(x.device)))
+    return d, sq, dmin, zq
+
+
+def dequantize(q_type: int, qweight, d, sq, dmin, zq, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """dequantize_linear_weight (quant_utils.py:277-310)."""
+    L.require_cuda(qweight, d, sq, dmin, zq)
+    d_row, d_col = qweight.shape
+    out = torch.empty(d_row, d_col, dtype=out_dtype, device=qweight.device)
+    L.check(L.load().gq_dequantize(int(q_type), L.ptr(qweight.contiguous()), L.ptr(d.contiguous()), L.ptr(sq.contiguous()),
+                                   L.ptr(dmin.contiguous()), L.ptr(zq.contiguous()), d_row, d_col, L.ptr(out),
+                                   L.dtype_code(out_dtype), L.stream_of(qweight.device)))
+    return out
+
+
+def pack(q_type: int, qweight, d, sq, dmin=None, zq=None) -> torch.Tensor:
+    """pack_Q*K (packing_utils.py:33-326) -> (d_row, d_col/256*type_size) uint8 on the device."""
+    L.require_cuda(qweight, d, sq, dmin, zq)
+    d_row, d_col = qweight.shape
+    f = L.format_info(q_type)
+    out = torch.empty(d_row, d_col // QK_K * f["type_size"], dtype=torch.uint8, device=qweight.device)
+    keep = [qweight.contiguous(), d.contiguous(), sq.contiguous(),
+            dmin.contiguous() if dmin is not None else None, zq.contiguous() if zq is not None else None]
+    L.check(L.load().gq_pack(int(q_type), L.ptr(keep[0]), L.ptr(keep[1]), L.ptr(keep[2]), L.ptr(keep[3]), L.ptr(keep[4]),
+                             d_row, d_col, L.ptr(out), L.stream_of(qweight.device)))
+    return out

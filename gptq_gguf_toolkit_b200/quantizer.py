@@ -1,0 +1,444 @@
+"""Block-sequential quantisation driver -- host-side mirror of the reference's
+quant/gptq/src/quantizer.py::Quantizer (same constructor arguments, same quantize(quant_config) call, same
+<save_dir>/<module name>/data.pth schema, quantizer.py:120-128,206-214,267-275).
+
+What is different (B200-first, results unchanged):
+  * the per-layer work runs in libgq (include/gq.h) instead of torch loops;
+  * layers of a block that see the same input tensor (q/k/v, gate/up) share ONE Hessian and ONE U, and,
+    when they also share the q_type, are quantised as one stacked matrix in one kernel launch (rows of a
+    GPTQ problem are independent given U, so the outputs are bit-identical to separate calls);
+  * calibration sequences of equal length are pushed through a block in batches (`calibration_batch_size`)
+    instead of one at a time (GPTQ.update already weights a batch by its number of sequences, gptq.py:110-111);
+  * multi-GPU (torch.distributed, NCCL): every rank holds its slice of the calibration sequences (as in the
+    reference, quant.py:177-179), Hessians are all-reduced (gptq.py:131-132), then -- unlike the reference,
+    where rank 0 quantises alone -- every rank quantises a ROW SLICE of each projection and the results are
+    all-gathered; rank 0 alone writes data.pth.
+"""
+from __future__ import annotations
+
+import os
+import threading
+import queue
+from typing import Any, Dict, Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import ops
+from .gptq import GPTQ, HessianAccumulator
+from .model_utils import ForwardInterrupt, InputCollector, LINEAR_LAYERS, maybe_first_element, select_layers, to
+from .quant_utils import GGML_QUANT_SIZES, GGMLQuantizationType
+
+
+def _dist_on() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def _rank() -> int:
+    return dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+
+
+def _world() -> int:
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
+class PhaseTimer:
+    """CUDA-event phase timing without synchronising inside the run; totals() syncs once at the end."""
+
+    def __init__(self, enabled: bool = True):
+        self.enabled = enabled and torch.cuda.is_available()
+        self.spans: Dict[str, list] = {}
+
+    def span(self, name: str):
+        timer = self
+
+        class _Span:
+            def __enter__(self_inner):
+                if timer.enabled:
+                    self_inner.a = torch.cuda.Event(enable_timing=True)
+                    self_inner.b = torch.cuda.Event(enable_timing=True)
+                    self_inner.a.record()
+                return self_inner
+
+            def __exit__(self_inner, *exc):
+                if timer.enabled:
+                    self_inner.b.record()
+                    timer.spans.setdefault(name, []).append((self_inner.a, self_inner.b))
+                return False
+
+        return _Span()
+
+    def totals(self) -> Dict[str, float]:
+        if not self.enabled:
+            return {}
+        torch.cuda.synchronize()
+        return {k: sum(a.elapsed_time(b) for a, b in v) / 1e3 for k, v in self.spans.items()}
+
+
+class _AsyncSaver:
+    """torch.save on a worker thread so that file I/O overlaps GPU work (the reference saves inline)."""
+
+    def __init__(self):
+        self.q: "queue.Queue" = queue.Queue(maxsize=16)
+        self.err: Optional[BaseException] = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        while True:
+            item = self.q.get()
+            if item is None:
+                return
+            obj, path, ready = item
+            try:
+                ready.synchronize()     # the D2H copies were enqueued before this event
+                os.makedirs(os.path.dirname(path), exist_ok=True)
+                torch.save(obj, path)
+            except BaseException as e:  # noqa: BLE001
+                self.err = e
+
+    def submit(self, obj, path, ready):
+        self.q.put((obj, path, ready))
+
+    def close(self):
+        self.q.put(None)
+        self.t.join()
+        if self.err is not None:
+            raise self.err
+
+
+class Quantizer:
+    def __init__(self, model: nn.Module, data_loader: Iterable, quantizable_modules: str,
+                 quantizer_kwargs: Dict[str, Any], pre_block_modules: List[str], post_block_modules: List[str],
+                 block_modules: str, save_dir: Optional[str], quant_non_block_modules: bool = False,
+                 device: Optional[torch.device] = None, cpu_offload_modules: bool = False,
+                 cpu_offload_activations: bool = False, verbose: bool = False,
+                 # ---- additions over the reference ----
+                 calibration_batch_size: int = 8, share_hessians: bool = True, keep_results: bool = False,
+                 save_packed: bool = True, timer: Optional[PhaseTimer] = None) -> None:
+        self.model = model
+        self.data_loader = data_loader
+        self.quantizable_modules = quantizable_modules
+        self.quantizer_kwargs = dict(quantizer_kwargs)
+        self.pre_block_modules = pre_block_modules
+        self.post_block_modules = post_block_modules
+        self.block_modules = block_modules
+        self.device = device
+        self.cpu_offload_modules = cpu_offload_modules
+        self.cpu_offload_activations = cpu_offload_activations
+        self.quant_non_block_modules = quant_non_block_modules
+        self.verbose = verbose
+        self.save_dir = save_dir
+        self.calibration_batch_size = max(1, int(calibration_batch_size))
+        self.share_hessians = share_hessians
+        self.keep_results = keep_results
+        self.save_packed = save_packed
+        self.timer = timer or PhaseTimer(False)
+        self.results: Dict[str, Dict[str, Any]] = {}    # module name -> data.pth dict (+ "packed"), if keep_results
+        self.non_invertible: List[str] = []
+        self._saver: Optional[_AsyncSaver] = None
+
+    # -------------------------------------------------------------------------------------------
+    def _log(self, msg: str):
+        if self.verbose and _rank() == 0:
+            print(msg, flush=True)
+
+    def _get_submodule(self, module_name: str):
+        return self.model.get_submodule(module_name)
+
+    def _create_handle(self, layer, hessian: Optional[HessianAccumulator] = None):
+        return GPTQ(layer, hessian=hessian, **self.quantizer_kwargs)          # quantizer.py:239-240
+
+    # -------------------------------------------------------------------------------------------
+    def _emit(self, name: str, q_type, five, packed):
+        """data.pth schema of the reference (quantizer.py:267-275) + optional 'packed' GGUF bytes; rank 0 writes."""
+        if _rank() != 0:
+            return
+        if self.save_dir is None and not self.keep_results:
+            return
+        qweight, d, sq, dmin, zq = five
+
+        def host(t):   # pinned destination => the copy is truly asynchronous (torch caches pinned blocks)
+            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            buf.copy_(t, non_blocking=True)
+            return buf
+
+        with self.timer.span("save_d2h"):
+            obj = {
+                "q_type": int(q_type),
+                "qweight": host(qweight),
+                "super_group_scale": host(d),
+                "super_group_zero": host(dmin),
+                "group_scale_quant": host(sq),
+                "group_zero_quant": host(zq),
+            }
+            if self.save_packed and packed is not None:
+                obj["packed"] = host(packed)
+            ready = torch.cuda.Event()
+            ready.record()
+        if self.keep_results:
+            self.results[name] = obj
+        if self.save_dir is not None:
+            self._saver.submit(obj, os.path.join(self.save_dir, name, "data.pth"), ready)
+
+    # -------------------------------------------------------------------------------------------
+    def _quant_non_block_module(self, name: str, module: nn.Module, quant_config):
+        """quantizer.py:94-128 / 181-214 / 278-330: RTN K-quant of embed_tokens / lm_head (default Q6_K)."""
+        q_type = quant_config.get(name.split(".")[-1], GGMLQuantizationType.Q6_K)
+        kw = self.quantizer_kwargs
+        w = module.weight.data
+        with self.timer.span("rtn"):
+            qweight, d, sq, dmin, zq, packed, wdeq = ops.rtn_quantize(
+                w.contiguous(), int(q_type), kw.get("rmin", -1.0), kw.get("rdelta", 0.1), kw.get("nstep", 20),
+                packed=self.save_packed, wdeq_dtype=w.dtype)
+            module.weight.data = wdeq
+        self._emit(name, q_type, (qweight, d, sq, dmin, zq), packed)
+
+    # -------------------------------------------------------------------------------------------
+    def _prepare_hooks_and_handles(self, layers: Dict[str, nn.Module]):
+        """quantizer.py:222-237, plus Hessian sharing: layers that receive the very same input tensor object
+        during a forward are attached to one accumulator, which is updated once per forward."""
+        handles: Dict[str, GPTQ] = {}
+        hooks = {}
+        seen: list = []      # [(input tensor, accumulator)] of the forward in flight (refs keep addresses unique)
+        grouping_done = {"v": False}
+
+        def make_hook(name):
+            def _hook(_, inp, out):
+                x = inp[0]
+                h = handles[name]
+                if not self.share_hessians:
+                    h.update(x)
+                    return
+                for t, acc in seen:
+                    if t is x:
+                        if h.hessian is not acc:
+                            if grouping_done["v"]:
+                                raise RuntimeError(f"inconsistent input sharing for {name}")
+                            h.hessian.users -= 1
+                            h.hessian = acc
+                            acc.users += 1
+                        return
+                h.update(x)
+                seen.append((x, h.hessian))
+            return _hook
+
+        for layer_name, layer in layers.items():
+            handles[layer_name] = self._create_handle(layer)
+            hooks[layer_name] = layer.register_forward_hook(make_hook(layer_name))
+
+        def end_of_forward():
+            seen.clear()
+            grouping_done["v"] = True
+
+        return handles, hooks, end_of_forward
+
+    # -------------------------------------------------------------------------------------------
+    def _quant_group(self, handles: Dict[str, GPTQ], quant_config):
+        """quantizer.py:242-275.  Handles are processed per shared accumulator; same-q_type members of a group are
+        stacked row-wise into one launch, and with several ranks each rank takes a row slice."""
+        groups: Dict[int, List[str]] = {}
+        for name, h in handles.items():
+            groups.setdefault(id(h.hessian), []).append(name)
+        kw = self.quantizer_kwargs
+        rank, world = _rank(), _world()
+        for names in groups.values():
+            hs = [handles[n] for n in names]
+            acc = hs[0].hessian
+            with self.timer.span("allreduce"):
+                acc.all_reduce()                                               # gptq.py:131-132
+            q_types = [quant_config.get(n.split(".")[-1], GGMLQuantizationType.Q4_K) for n in names]  # quantizer.py:249
+            dtype = hs[0].layer.weight.dtype
+            # fp32 working copy of all members, stacked row-wise (gptq.py:138)
+            rows = [h.d_row for h in hs]
+            with self.timer.span("prepare"):
+                W = torch.cat([h.layer.weight.data.float() for h in hs], dim=0).contiguous()
+                ops.pre_step(acc.H, W)                                         # gptq.py:134-141
+                masks = torch.stack([(w == 0).all(dim=0) for w in W.split(rows, dim=0)])
+                if len(hs) > 1 and not bool((masks == masks[0:1]).all()):
+                    raise RuntimeError("layers sharing an input have different all-zero weight columns; "
+                                       "rerun with share_hessians=False")
+                U, not_pd = ops.prepare(acc.H, W, kw.get("rel_damp", 1e-2))    # gptq.py:305-324
+            # sub-groups of equal q_type, keeping module order
+            by_type: Dict[int, List[int]] = {}
+            for i, qt in enumerate(q_types):
+                by_type.setdefault(int(qt), []).append(i)
+            offs = [0]
+            for r in rows:
+                offs.append(offs[-1] + r)
+            for qt, idxs in by_type.items():
+                self._log(f"Quantizing {[names[i] for i in idxs]} with {GGMLQuantizationType(qt).name}.")
+                Wg = W if len(idxs) == len(hs) else torch.cat([W[offs[i]:offs[i + 1]] for i in idxs], 0).contiguous()
+                with self.timer.span("gptq"):
+                    outs = self._sharded_gptq(Wg, U, qt, dtype, rank, world)
+                qweight, d, sq, dmin, zq, packed, wdeq = outs
+                r0 = 0
+                for i in idxs:
+                    r1 = r0 + rows[i]
+                    h = hs[i]
+                    h.layer.weight.data = wdeq[r0:r1].clone() if len(idxs) > 1 else wdeq[r0:r1]   # quantizer.py:257-264
+                    self._emit(names[i], qt, (qweight[r0:r1], d[r0:r1], sq[r0:r1], dmin[r0:r1], zq[r0:r1]),
+                               packed[r0:r1] if packed is not None else None)
+                    r0 = r1
+            self._not_pd_flags.append((names, not_pd))
+            for h in hs:
+                h.reset()                                                      # quantizer.py:265
+
+    def _sharded_gptq(self, W, U, qt, dtype, rank, world):
+        kw = self.quantizer_kwargs
+        args = dict(block_size=kw.get("block_size", 128) or W.shape[1], rmin=kw.get("rmin", -1.0),
+                    rdelta=kw.get("rdelta", 0.1), nstep=kw.get("nstep", 20), packed=True, wdeq_dtype=dtype)
+        if world == 1:
+            return ops.gptq_quantize(W, U, qt, **args)[:7]
+        total = W.shape[0]
+        per = -(-total // world)
+        per = -(-per // 32) * 32                     # row slices in units of the kernel's 32-row CTA tile
+        lo, hi = min(rank * per, total), min((rank + 1) * per, total)
+        Wl = torch.zeros(per, W.shape[1], dtype=W.dtype, device=W.device)
+        Wl[: hi - lo] = W[lo:hi]
+        outs = ops.gptq_quantize(Wl, U, qt, **args)[:7]
+        with self.timer.span("allgather"):
+            full = []
+            for t in outs:
+                g = torch.empty((world * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+                dist.all_gather_into_tensor(g, t.contiguous())
+                full.append(g[:total])
+        return tuple(full)
+
+    # -------------------------------------------------------------------------------------------
+    def _batched_inputs(self, input_args, input_kwargs):
+        """Merge per-sequence captures into batches when they only differ in hidden_states."""
+        bs = self.calibration_batch_size
+        n = len(input_args)
+        ok = bs > 1 and n > 1 and all(len(a) == 1 and isinstance(a[0], torch.Tensor) for a in input_args)
+        if ok:
+            shp = input_args[0][0].shape
+            ok = all(a[0].shape == shp and a[0].shape[0] == 1 for a in input_args)
+        if ok:
+            k0 = input_kwargs[0]
+            for k in input_kwargs[1:]:
+                if k.keys() != k0.keys():
+                    ok = False
+                    break
+                for key, v in k.items():
+                    v0 = k0[key]
+                    if isinstance(v, torch.Tensor):
+                        if not (isinstance(v0, torch.Tensor) and v.shape == v0.shape and torch.equal(v, v0)):
+                            ok = False
+                    elif isinstance(v, (tuple, list)) and all(isinstance(t, torch.Tensor) for t in v):
+                        if not all(torch.equal(a, b) for a, b in zip(v, v0)):
+                            ok = False
+                    elif v is not v0 and v != v0:
+                        ok = False
+                if not ok:
+                    break
+        if not ok:
+            return [(list(a), k) for a, k in zip(input_args, input_kwargs)]
+        hs = torch.cat([a[0] for a in input_args], dim=0)
+        return [([hs[i:i + bs]], input_kwargs[0]) for i in range(0, n, bs)]
+
+    # -------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def quantize(self, quant_config: Dict[str, GGMLQuantizationType]) -> None:
+        device = self.device or next(self.model.parameters()).device
+        self._not_pd_flags = []
+        if self.save_dir is not None and _rank() == 0:
+            os.makedirs(self.save_dir, exist_ok=True)
+            self._saver = _AsyncSaver()
+        blocks = self._get_submodule(self.block_modules)
+        pre_blocks = [(n, self._get_submodule(n)) for n in self.pre_block_modules]
+        post_blocks = [(n, self._get_submodule(n)) for n in self.post_block_modules]
+        blocks[0] = blocks[0].to(device)
+        for _, module in pre_blocks:
+            module.to(device)
+        use_cache = None
+        if hasattr(self.model.config, "use_cache"):
+            use_cache = self.model.config.use_cache
+            self.model.config.use_cache = False
+
+        # ---- capture the inputs of block 0 (quantizer.py:78-89) ----
+        with self.timer.span("capture"):
+            blocks[0] = InputCollector(blocks[0], cpu_offload=self.cpu_offload_activations)
+            for inp_args, inp_kwargs in self.data_loader:
+                try:
+                    self.model(*to(inp_args, device=device), **to(inp_kwargs, device=device))
+                except ForwardInterrupt:
+                    pass
+            input_args = blocks[0].input_args
+            input_kwargs = blocks[0].input_kwargs
+            blocks[0] = blocks[0].module
+            batches = self._batched_inputs(input_args, input_kwargs)
+            del input_args, input_kwargs
+        if _dist_on():
+            dist.barrier()
+
+        # ---- pre-block modules (quantizer.py:94-128) ----
+        for name, module in pre_blocks:
+            if not self.quant_non_block_modules:
+                continue
+            self._log(f"Processing {name}.")
+            self._quant_non_block_module(name, module.to(device), quant_config)
+        if self.cpu_offload_modules:
+            for _, module in pre_blocks:
+                module.cpu()
+
+        # ---- transformer blocks (quantizer.py:137-179) ----
+        for block_id, block in enumerate(blocks):
+            self._log(f"Processing {self.block_modules} {block_id}/{len(blocks)}.")
+            block = block.to(device)
+            layer_prefix = f"{self.block_modules}.{block_id}."
+            layers = select_layers(self.model, layer_prefix, self.quantizable_modules, LINEAR_LAYERS)
+            handles, hooks, end_of_forward = self._prepare_hooks_and_handles(layers)
+
+            with self.timer.span("forward1"):
+                for inp_args, inp_kwargs in batches:
+                    block(*to(inp_args, device=device), **to(inp_kwargs, device=device))
+                    end_of_forward()
+            for h in hooks.values():
+                h.remove()
+
+            self._quant_group(handles, quant_config)
+
+            with self.timer.span("forward2"):
+                for inp_args, inp_kwargs in batches:
+                    out = block(*to(inp_args, device=device), **to(inp_kwargs, device=device))
+                    out = maybe_first_element(out)
+                    if self.cpu_offload_activations:
+                        out = out.cpu()
+                    if len(inp_args) > 0:                                     # quantizer.py:167-168
+                        if inp_args[0].shape == out.shape and inp_args[0].device == out.device:
+                            inp_args[0].copy_(out)      # in place: batches are views of one activation buffer
+                        else:
+                            inp_args[0] = out
+                    elif "hidden_states" in inp_kwargs:
+                        inp_kwargs["hidden_states"] = out
+                    else:
+                        raise ValueError("Unsupported block input format.")
+            if self.cpu_offload_modules:
+                block = block.cpu()
+            del handles, hooks
+
+        # ---- post-block modules (quantizer.py:181-214) ----
+        for name, module in post_blocks:
+            if not self.quant_non_block_modules:
+                continue
+            self._log(f"Processing {name}")
+            self._quant_non_block_module(name, module.to(device), quant_config)
+
+        if use_cache is not None:
+            self.model.config.use_cache = use_cache
+        if self._saver is not None:
+            with self.timer.span("save_wait"):
+                self._saver.close()
+            self._saver = None
+        if _dist_on():
+            dist.barrier()
+
+    def non_invertible_modules(self) -> List[str]:
+        """Modules whose Hessian was not positive definite (U fell back to identity, gptq.py:321-323). Synchronises."""
+        out = []
+        for names, flag in self._not_pd_flags:
+            if bool(flag.item()):
+                out.extend(names)
+        return out

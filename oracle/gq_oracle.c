@@ -100,7 +100,7 @@ static void group_weights(const float *x, int n, float *w) {
 }
 
 static void make_k_quants_call(const float *x, long row_stride, int rows, int n, int maxq,
-                               float rmin, float rdelta, int nstep,
+                               double rmin, double rdelta, int nstep,
                                float *scale_out, float *zero_out, uint32_t *flags) {
     const int gpr = QK_K / n;           /* groups per row */
     const long G = (long)rows * gpr;
@@ -136,7 +136,7 @@ static void make_k_quants_call(const float *x, long row_stride, int rows, int n,
     if (nstep >= 1) {                                 /* :235 */
         for (int i = 0; i <= nstep; ++i) {            /* :240 */
             /* python double arithmetic, then cast to fp32 when multiplied into the tensor */
-            const float num = (float)((double)rmin + (double)rdelta * (double)i + (double)maxq);
+            const float num = (float)(rmin + rdelta * (double)i + (double)maxq);
             int any_valid = 0;
 #pragma omp parallel for schedule(static) reduction(| : any_valid)
             for (long g = 0; g < G; ++g) {
@@ -225,7 +225,7 @@ static void make_quants_call(const float *x, long row_stride, int rows, int n, i
  *                      bit i of flags[1] = candidate i was accepted by some group.
  * ---------------------------------------------------------------------------------------- */
 int orc_get_scale_and_zero(const float *x, long row_stride, int rows, int qtype,
-                           float rmin, float rdelta, int nstep,
+                           double rmin, double rdelta, int nstep,
                            uint16_t *d, long d_stride, uint16_t *dmin, long dmin_stride,
                            uint8_t *sq, long sq_stride, uint8_t *zq, long zq_stride,
                            uint32_t *flags) {
@@ -277,7 +277,7 @@ static inline float code_to_f(uint8_t b, int is_signed) { return is_signed ? (fl
  * bits; sq,zq (d_row, d_col/group_size).
  * ---------------------------------------------------------------------------------------- */
 int orc_gptq_step(float *W, const float *U, long u_rs, long u_cs, int d_row, int d_col, int qtype,
-                  int block_size, float rmin, float rdelta, int nstep,
+                  int block_size, double rmin, double rdelta, int nstep,
                   uint8_t *qweight, uint16_t *d, uint16_t *dmin, uint8_t *sq, uint8_t *zq,
                   uint32_t *flags /* 2 per super-block or NULL */) {
     orc_fmt_t f;
@@ -357,7 +357,7 @@ int orc_gptq_step(float *W, const float *U, long u_rs, long u_cs, int d_row, int
  * W is read-only.
  * ---------------------------------------------------------------------------------------- */
 int orc_rtn_quantize(const float *W, int d_row, int d_col, int qtype,
-                     float rmin, float rdelta, int nstep,
+                     double rmin, double rdelta, int nstep,
                      uint8_t *qweight, uint16_t *d, uint16_t *dmin, uint8_t *sq, uint8_t *zq) {
     orc_fmt_t f;
     if (orc_fmt(qtype, &f)) return -1;

@@ -72,7 +72,7 @@ def get_scale_and_zero(x: np.ndarray, qtype: int, rmin=-1.0, rdelta=0.1, nstep=2
     flags = np.zeros(2, np.uint32)
     rc = lib().orc_get_scale_and_zero(
         _p(x, C.c_float), C.c_long(QK_K), C.c_int(rows), C.c_int(qtype),
-        C.c_float(rmin), C.c_float(rdelta), C.c_int(nstep),
+        C.c_double(rmin), C.c_double(rdelta), C.c_int(nstep),
         _p(d, C.c_uint16), C.c_long(1), _p(dmin, C.c_uint16), C.c_long(1),
         _p(sq, C.c_uint8), C.c_long(gpr), _p(zq, C.c_uint8), C.c_long(gpr), _p(flags, C.c_uint32))
     assert rc == 0
@@ -100,7 +100,7 @@ def gptq_step(W: np.ndarray, U: np.ndarray, qtype: int, block_size=128, rmin=-1.
     rc = lib().orc_gptq_step(
         _p(Wc, C.c_float), _p(U, C.c_float), C.c_long(rs), C.c_long(cs),
         C.c_int(d_row), C.c_int(d_col), C.c_int(qtype), C.c_int(block_size),
-        C.c_float(rmin), C.c_float(rdelta), C.c_int(nstep),
+        C.c_double(rmin), C.c_double(rdelta), C.c_int(nstep),
         _p(qw, C.c_uint8), _p(d, C.c_uint16), _p(dmin, C.c_uint16), _p(sq, C.c_uint8), _p(zq, C.c_uint8),
         _p(flags, C.c_uint32))
     assert rc == 0, rc
@@ -122,7 +122,7 @@ def rtn_quantize(W: np.ndarray, qtype: int, rmin=-1.0, rdelta=0.1, nstep=20):
     zq = np.empty((d_row, ng), np.uint8)
     rc = lib().orc_rtn_quantize(
         _p(W, C.c_float), C.c_int(d_row), C.c_int(d_col), C.c_int(qtype),
-        C.c_float(rmin), C.c_float(rdelta), C.c_int(nstep),
+        C.c_double(rmin), C.c_double(rdelta), C.c_int(nstep),
         _p(qw, C.c_uint8), _p(d, C.c_uint16), _p(dmin, C.c_uint16), _p(sq, C.c_uint8), _p(zq, C.c_uint8))
     assert rc == 0, rc
     cd = _code_dtype(qtype)
