@@ -31,6 +31,7 @@ SIGNATURES = {
     "gq_last_error": (C.c_char_p, []),
     "gq_format_info": (_i, [_i, C.POINTER(_i)]),
     "gq_device_count": (_i, []),
+    "gq_launch_count": (_l, []),
     "gq_hessian_workspace_bytes": (_sz, [_l, _i, _i]),
     "gq_hessian_update": (_i, [_vp, _vp, _l, _i, _i, _f, _f, _vp, _sz, _vp]),
     "gq_pre_step": (_i, [_vp, _vp, _i, _i, _vp]),

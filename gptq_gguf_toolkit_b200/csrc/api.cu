@@ -4,9 +4,16 @@
 
 #include "common.cuh"
 
+#include <atomic>
+
 namespace {
 thread_local char g_err[512] = "";
+std::atomic<long> g_launches{0};
 }
+
+void gq_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+extern "C" long gq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 void gq_set_error(const char *fmt, ...) {
     va_list ap;

@@ -47,6 +47,7 @@ struct SearchParams {
 // error plumbing (thread-local message, never throws)
 // ---------------------------------------------------------------------------------------------
 void gq_set_error(const char *fmt, ...);
+void gq_count_launches(int n);   // bookkeeping behind gq_launch_count()
 #define GQ_CHECK_CUDA(expr)                                                              \
     do {                                                                                 \
         cudaError_t _e = (expr);                                                         \

@@ -273,6 +273,7 @@ template <int QT> int launch_layer(const LayerParams &p, cudaStream_t st) {
     GQ_CHECK_CUDA(cudaFuncSetAttribute(gptq_layer_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (p.d_row + R - 1) / R;
     gptq_layer_kernel<QT><<<grid, NT, smem, st>>>(p);
+    gq_count_launches(1);
     GQ_CHECK_CUDA(cudaGetLastError());
     return GQ_OK;
 }

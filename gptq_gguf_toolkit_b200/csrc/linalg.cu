@@ -187,6 +187,7 @@ extern "C" int gq_pre_step(float *H, float *W, int d_row, int d_col, gq_stream_t
     cudaStream_t st = (cudaStream_t)stream;
     zero_dead_cols_kernel<<<ew_grid((long)d_row * d_col), 256, 0, st>>>(H, W, d_row, d_col);
     fix_dead_diag_kernel<<<(d_col + 255) / 256, 256, 0, st>>>(H, d_col);
+    gq_count_launches(2);
     GQ_CHECK_CUDA(cudaGetLastError());
     return GQ_OK;
 }
@@ -222,13 +223,16 @@ extern "C" int gq_prepare(float *H, const float *W, int d_row, int d_col, float 
     }
     mask_zero_cols_kernel<<<ew_grid((long)n * n), 256, 0, st>>>(H, n, nz);
     damp_kernel<<<1, 1024, 0, st>>>(H, n, rel_damp);
+    gq_count_launches(3);
 
     // --- L = chol(J H J), level-0 blocks of inv(L) ---
     reverse_copy_kernel<<<ew_grid((long)n * n), 256, 0, st>>>(H, A, n);
+    gq_count_launches(1);
     GQ_CHECK_CUDA(cudaMemsetAsync(Li, 0, (size_t)n * n * sizeof(float), st));
     GQ_CHECK_CUDA(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DiagSmem)));
     for (int k0 = 0; k0 < n; k0 += NB) {
         chol_diag_kernel<<<1, DT, sizeof(DiagSmem), st>>>(A, Li, ld, k0, flag);
+        gq_count_launches(1);
         const int rem = n - k0 - NB;
         if (rem > 0) {
             float *P = A + (size_t)(k0 + NB) * ld + k0;          // panel (rem x 128)
@@ -273,6 +277,7 @@ extern "C" int gq_prepare(float *H, const float *W, int d_row, int d_col, float 
     }
 
     finish_u_kernel<<<ew_grid((long)n * n), 256, 0, st>>>(Li, U_out, n, flag);
+    gq_count_launches(not_pd_flag ? 2 : 1);
     if (not_pd_flag) copy_flag_kernel<<<1, 1, 0, st>>>(flag, not_pd_flag);
     GQ_CHECK_CUDA(cudaGetLastError());
     return GQ_OK;

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(NT) rtn_kernel(const RtnParams p) {
 template <int QT> int launch_rtn(const RtnParams &p, cudaStream_t st) {
     dim3 grid((p.d_row + R - 1) / R, p.nsb);
     rtn_kernel<QT><<<grid, NT, 0, st>>>(p);
+    gq_count_launches(1);
     GQ_CHECK_CUDA(cudaGetLastError());
     return GQ_OK;
 }

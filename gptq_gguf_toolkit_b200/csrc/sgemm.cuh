@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(NT) sgemm_kernel(const Args a) {
 inline int launch(const Args &a, int batch, cudaStream_t st) {
     dim3 grid(a.N / BN, a.M / BM, batch);
     sgemm_kernel<<<grid, NT, 0, st>>>(a);
+    gq_count_launches(1);
     GQ_CHECK_CUDA(cudaGetLastError());
     return GQ_OK;
 }

@@ -68,6 +68,9 @@ GQ_API int gq_format_info(int qtype, int out7[7]);
 /* Number of CUDA devices visible (0 when there is none; never an error). */
 GQ_API int gq_device_count(void);
 
+/* Number of CUDA kernels this library has launched in this process so far (bench.py's gpu_launches). */
+GQ_API long gq_launch_count(void);
+
 /* H <- beta*H + alpha * X^T X   -- replaces GPTQ.update's addmm_ (gptq.py:110-112).
  * X: (n_tok, d_col) of x_dtype, row-major, contiguous.  H: (d_col, d_col) fp32, kept fully symmetric.
  * bf16 inputs take the tcgen05 path (products exact in fp32, fp32 accumulation in TMEM);
