@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's headline metric: wall-clock seconds to GPTQ-quantise a random-init
+Llama-3-8B (bf16) to uniform Q4_K with 128 x 2048 synthetic calibration tokens, on N B200s.
+
+    python bench.py --gpus 1 --steps 1 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
+
+One "step" = one complete quantisation of the model through gptq_gguf_toolkit_b200.quantizer.Quantizer
+(capture block inputs, per block: forward pass 1 + Hessians, Cholesky chain, fused column loop, forward
+pass 2; embed_tokens / lm_head RTN), weights restored to the pristine random init before every step.
+  value : weights and token ids resident in HBM when the timed region starts, results left in HBM.
+  e2e   : the same call with HOST buffers: pristine weights are copied from pinned host memory inside the
+          timed region and every result (five tensors + GGUF bytes per module) is read back to pinned host memory.
+Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "llama3_8b_q4k_quantize_wall_clock_s"
+REGEX = r".*layers.*((q|k|v|o|gate|up|down)_proj)$"
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "llama3-8b": dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32,
+                      num_key_value_heads=8, vocab_size=128256, max_position_embeddings=8192, n_seq=128, seq_len=2048,
+                      dtype="bfloat16"),
+    # development only (NOT the reported metric): same layer shapes, fewer blocks / sequences
+    "llama3-8b-dev": dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=2, num_attention_heads=32,
+                          num_key_value_heads=8, vocab_size=128256, max_position_embeddings=8192, n_seq=32, seq_len=2048,
+                          dtype="bfloat16"),
+    # BASELINE.json configs[0] (plumbing)
+    "tiny": dict(hidden_size=256, intermediate_size=768, num_hidden_layers=2, num_attention_heads=4,
+                 num_key_value_heads=2, vocab_size=1024, max_position_embeddings=256, n_seq=8, seq_len=128,
+                 dtype="float32"),
+}
+
+
+def layer_shapes(w):
+    h, i = w["hidden_size"], w["intermediate_size"]
+    kv = h // w["num_attention_heads"] * w["num_key_value_heads"]
+    return [("q_proj", h, h), ("k_proj", kv, h), ("v_proj", kv, h), ("o_proj", h, h),
+            ("gate_proj", i, h), ("up_proj", i, h), ("down_proj", h, i)]
+
+
+def algorithmic_work(w):
+    """rank-k flops d_row*d_col*(d_col-128) per layer; Hessian flops 2*T*d_col^2 per layer as the
+    reference computes it (7 per block)."""
+    T = w["n_seq"] * w["seq_len"]
+    rk = sum(r * c * (c - 128) for _, r, c in layer_shapes(w)) * w["num_hidden_layers"]
+    hs = sum(2 * T * c * c for _, r, c in layer_shapes(w)) * w["num_hidden_layers"]
+    return rk, hs
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tf=d["bf16_tflops_sustained"], tf_burst=d["bf16_tflops"], source="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(hbm_gbs=6650.0, tf=1400.0, tf_burst=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if x > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# =================================================================================================
+# reference arm / cpu_baseline: the reference's CPU implementation of the hot path.
+# The reference is pure Python on torch and cannot travel to the GPU box, so this is the oracle PORT:
+# torch CPU ops for exactly the library calls the reference makes (H.addmm_, cholesky / cholesky_inverse /
+# cholesky(upper)), the C restatement (oracle/gq_oracle.c, OpenMP over rows) for the column loop.
+# =================================================================================================
+def cpu_reference_sample(w, threads: int):
+    """Times a bounded sample (~10-30 s) and extrapolates each phase by its algorithmic work to the whole model.
+    Returns (whole_model_hot_path_seconds, detail)."""
+    from oracle import oracle as orc
+    import numpy as np
+    torch.set_num_threads(threads)
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    g = torch.Generator().manual_seed(0)
+    shapes = layer_shapes(w)
+    dcols = sorted({c for _, _, c in shapes})
+    L, nblk, nseq = w["seq_len"], w["num_hidden_layers"], w["n_seq"]
+    detail = {}
+    # 1. Hessian: one H.addmm_ per calibration sequence, measured at every distinct d_col (gptq.py:108-112)
+    t_h = {}
+    for c in dcols:
+        x = torch.randn(L, c, generator=g).to(torch.bfloat16).float()
+        H = torch.zeros(c, c)
+        H.addmm_(x.T, x, beta=0.0, alpha=2.0)            # warm
+        t0 = time.perf_counter()
+        H.addmm_(x.T, x, beta=0.5, alpha=1.0)
+        t_h[c] = time.perf_counter() - t0
+    hess = sum(t_h[c] for _, _, c in shapes) * nseq * nblk
+    detail["hessian_s_per_seq"] = {str(k): round(v, 4) for k, v in t_h.items()}
+    # 2. Cholesky chain, measured at every distinct d_col (gptq.py:305-324)
+    t_p = {}
+    for c in dcols:
+        x = torch.randn(2 * c, c, generator=g)
+        H = (x.T @ x) / c + 0.01 * torch.eye(c)
+        t0 = time.perf_counter()
+        Hi = torch.cholesky_inverse(torch.linalg.cholesky(H))
+        torch.linalg.cholesky(Hi, upper=True)
+        t_p[c] = time.perf_counter() - t0
+    prep = sum(t_p[c] for _, _, c in shapes) * nblk
+    detail["prepare_s"] = {str(k): round(v, 3) for k, v in t_p.items()}
+    # 3. column loop: rows are independent => time(d_row, d_col) = d_row * f(d_col), f = a*d_col + b*d_col^2.
+    #    Fit a, b from 256-row slabs at two widths, then sum over the model's layers.
+    rows = 256
+    fs = {}
+    for c in (1024, 2048):
+        rng = np.random.default_rng(c)
+        W = (rng.standard_normal((rows, c)) * 0.02).astype(np.float32)
+        U = np.triu(rng.standard_normal((c, c)).astype(np.float32) * 0.01) + np.eye(c, dtype=np.float32)
+        t0 = time.perf_counter()
+        orc.gptq_step(W, U, 12)
+        fs[c] = (time.perf_counter() - t0) / rows
+    b = (fs[2048] / 2048 - fs[1024] / 1024) / (2048 - 1024)
+    a = fs[1024] / 1024 - b * 1024
+    step = sum(r * (a * c + b * c * c) for _, r, c in shapes) * nblk
+    detail["step_fit"] = {"a": a, "b": b, "s_per_row_1024": fs[1024], "s_per_row_2048": fs[2048]}
+    total = hess + prep + step
+    detail.update(hessian_s=round(hess, 1), prepare_s_total=round(prep, 1), step_s=round(step, 1))
+    return total, detail
+
+
+def run_reference_arm(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    for _ in range(max(0, args.warmup - 2)):      # the sample is deterministic CPU work; one warm-up is plenty
+        cpu_reference_sample(w, threads)
+    vals, detail = [], None
+    for _ in range(args.steps):
+        v, detail = cpu_reference_sample(w, threads)
+        vals.append(v)
+    v = sum(vals) / len(vals)
+    sample = ("per phase: H.addmm_ of one 2048-token sequence at each d_col, one Cholesky chain at each d_col, column loop on "
+              "256-row slabs at d_col 1024/2048 fitted to a*d_col+b*d_col^2; scaled by algorithmic work to 32 blocks x 7 "
+              "projections x 128 sequences (hot path only: no model forwards, no embed/lm_head)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload + " uniform Q4_K, CPU oracle port, extrapolated from a bounded sample", **{k: w[k] for k in ("n_seq", "seq_len")}},
+        "cpu_baseline": {"value": v, "unit": "s", "cores": threads, "kind": "port", "sample": sample, "detail": detail},
+        "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# =================================================================================================
+# own arm
+# =================================================================================================
+def build_model(w, device, seed=0):
+    from transformers import LlamaConfig, LlamaForCausalLM
+    cfg = LlamaConfig(**{k: w[k] for k in ("hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads",
+                                           "num_key_value_heads", "vocab_size", "max_position_embeddings")},
+                      tie_word_embeddings=False)
+    dtype = getattr(torch, w["dtype"])
+    torch.manual_seed(seed)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        with torch.device(device):
+            model = LlamaForCausalLM(cfg)
+    finally:
+        torch.set_default_dtype(old)
+    return model.eval()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", type=str, default="llama3-8b", choices=list(WORKLOADS))
+    ap.add_argument("--qtype", type=str, default="Q4_K")
+    ap.add_argument("--batch", type=int, default=8, help="calibration sequences per block forward")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        run_reference_arm(args, w)
+        return
+
+    import torch.distributed as dist
+    from gptq_gguf_toolkit_b200 import ops
+    from gptq_gguf_toolkit_b200.data_utils import synthetic_tokens
+    from gptq_gguf_toolkit_b200.quant import build_quant_config
+    from gptq_gguf_toolkit_b200.quantizer import PhaseTimer, Quantizer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group(backend="nccl", init_method="env://", device_id=device)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    model = build_model(w, device)
+    quant_config = build_quant_config(args.qtype, None)
+    names = [n for n, m in model.named_modules() if isinstance(m, torch.nn.Linear)] + ["model.embed_tokens"]
+    mods = {n: model.get_submodule(n) for n in names}
+    pristine = {n: m.weight.data.clone() for n, m in mods.items()}            # HBM copy (value runs)
+    tokens = synthetic_tokens(w["n_seq"], w["seq_len"], w["vocab_size"], seed=1)
+    per = len(tokens) // world
+    tokens = [t.to(device) for t in tokens[rank * per:(rank + 1) * per]]      # quant.py:177-179 slicing
+    loader = [([], {"input_ids": t}) for t in tokens]
+    host_w = None
+
+    def restore_from_hbm():
+        for n, m in mods.items():
+            m.weight.data = pristine[n].clone()
+
+    def one_step(e2e: bool):
+        timer = PhaseTimer(True)
+        q = Quantizer(model, data_loader=loader, quantizable_modules=REGEX,
+                      quantizer_kwargs=dict(rel_damp=0.01, block_size=128, act_order=False, quant_scale="absmax",
+                                            static_groups=False, rmin=-1.0, rdelta=0.1, nstep=20, verbose=False),
+                      pre_block_modules=["model.embed_tokens"], block_modules="model.layers", post_block_modules=["lm_head"],
+                      quant_non_block_modules=True, device=device, save_dir=None, keep_results=e2e,
+                      calibration_batch_size=args.batch, timer=timer)
+        if not e2e:
+            restore_from_hbm()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        l0 = ops.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        h2d = 0
+        if e2e:
+            for n, m in mods.items():
+                m.weight.data = host_w[n].to(device, non_blocking=True)
+                h2d += host_w[n].numel() * host_w[n].element_size()
+        q.quantize(quant_config)
+        ev1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        secs = ev0.elapsed_time(ev1) / 1e3
+        if world > 1:
+            t = torch.tensor([secs], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs = float(t.item())
+        d2h = 0
+        if e2e:
+            for obj in q.results.values():
+                d2h += sum(v.numel() * v.element_size() for v in obj.values() if isinstance(v, torch.Tensor))
+            q.results.clear()
+        bad = q.non_invertible_modules()
+        return secs, timer.totals(), ops.launch_count() - l0, h2d, d2h, bad
+
+    for _ in range(args.warmup):
+        one_step(False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    times, phases, launches, bad = [], {}, 0, []
+    for _ in range(args.steps):
+        secs, ph, nl, _, _, bad = one_step(False)
+        times.append(secs)
+        launches += nl
+        for k, v in ph.items():
+            phases[k] = phases.get(k, 0.0) + v / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    value = sum(times) / len(times)
+
+    e2e = None
+    if not args.no_e2e:
+        host_w = {n: t.to("cpu").pin_memory() for n, t in pristine.items()}
+        secs, _, _, h2d, d2h, _ = one_step(True)
+        e2e = {"value": secs, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": 1}
+
+    if rank == 0:
+        pk = peaks()
+        rk_flops, hs_flops = algorithmic_work(w)
+        t_gptq = phases.get("gptq", 0.0)
+        n_layer_launch = w["num_hidden_layers"] * 4      # q/k/v stacked, o, gate/up stacked, down
+        achieved = (rk_flops / world) / t_gptq / 1e12 if t_gptq > 0 else 0.0
+        roofline = {
+            "bound": "tensor", "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s",
+            "frac": achieved / pk["tf"], "traffic": None,
+            "kernel": "gptq_layer_kernel<Q4_K>: fused scale search + 128-step column loop + left-looking rank-k update + GGUF pack",
+            "launches_per_step": n_layer_launch, "avg_launch_ms": 1e3 * t_gptq / max(1, n_layer_launch),
+            "peak_source": pk["source"],
+            "note": ("exact mode: the rank-k update is an fp32 FFMA chain in the reference's order (bit-identical packed bytes), "
+                     "so it runs on the SIMT pipes (nominal 148 SMs x 128 FMA x 2 x clock ~ 72 TFLOP/s at 1.9 GHz), not on tensor "
+                     "cores; the reference's right-looking form is HBM-bound at 32 flop/B (~209 TFLOP/s ceiling)"),
+        }
+        hot = sum(phases.get(k, 0.0) for k in ("hessian", "prepare", "prepare_host", "gptq", "rtn"))
+        line = {
+            "metric": METRIC, "value": value, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: random-init {w['dtype']} Llama ({w['num_hidden_layers']} blocks, d_model {w['hidden_size']}), "
+                                   f"{w['n_seq']} calib seqs x {w['seq_len']}, uniform {args.qtype}, exact mode",
+                       "calibration_batch": args.batch, "l2": "inputs (16 GB weights + 2 GB activations) exceed the 126 MB L2; no flush needed",
+                       "parallelism": f"dp{world} over calibration sequences + row-sharded quantisation" if world > 1 else "single GPU"},
+            "roofline": roofline,
+            "phases_s": {k: round(v, 4) for k, v in sorted(phases.items())},
+            "hot_path_s": round(hot, 4),
+            "hessian_tflops": round(hs_flops / world / phases["hessian"] / 1e12, 1) if phases.get("hessian") else None,
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "non_invertible_modules": bad,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, detail = cpu_reference_sample(w, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "s", "cores": threads, "kind": "port",
+                                    "sample": "hot path only (Hessian + Cholesky chain + column loop), per-phase bounded samples scaled by "
+                                              "algorithmic work to the whole model; see bench.py cpu_reference_sample", "detail": detail}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

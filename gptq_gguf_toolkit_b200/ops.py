@@ -15,6 +15,29 @@ from . import _lib as L
 
 QK_K = 256
 _ws_cache: dict = {}
+_timer = None   # optional quantizer.PhaseTimer: per-op CUDA-event spans ("hessian", "prepare", "gptq", "rtn")
+
+
+def set_timer(timer) -> None:
+    global _timer
+    _timer = timer
+
+
+class _NullSpan:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def _span(name: str):
+    return _timer.span(name) if _timer is not None else _NullSpan()
+
+
+def launch_count() -> int:
+    """Kernels launched by libgq in this process so far."""
+    return int(L.load().gq_launch_count())
 
 
 def _workspace(device, nbytes: int) -> torch.Tensor:
@@ -57,8 +80,9 @@ def hessian_update(H: torch.Tensor, X: torch.Tensor, beta: float, alpha: float) 
     code = L.dtype_code(X.dtype)
     nws = lib.gq_hessian_workspace_bytes(n_tok, d_col, code)
     ws = _workspace(H.device, nws) if nws else None
-    L.check(lib.gq_hessian_update(L.ptr(H), L.ptr(X), n_tok, d_col, code, float(beta), float(alpha),
-                                  L.ptr(ws), nws, L.stream_of(H.device)))
+    with _span("hessian"):
+        L.check(lib.gq_hessian_update(L.ptr(H), L.ptr(X), n_tok, d_col, code, float(beta), float(alpha),
+                                      L.ptr(ws), nws, L.stream_of(H.device)))
 
 
 def pre_step(H: torch.Tensor, W: torch.Tensor) -> None:
@@ -79,8 +103,9 @@ def prepare(H: torch.Tensor, W: torch.Tensor, rel_damp: float) -> Tuple[torch.Te
     flag = torch.zeros(1, dtype=torch.int32, device=H.device)
     nws = lib.gq_prepare_workspace_bytes(d_col)
     ws = _workspace(H.device, nws)
-    L.check(lib.gq_prepare(L.ptr(H), L.ptr(W), d_row, d_col, float(rel_damp), L.ptr(U), L.ptr(ws), nws,
-                           L.ptr(flag), L.stream_of(H.device)))
+    with _span("prepare"):
+        L.check(lib.gq_prepare(L.ptr(H), L.ptr(W), d_row, d_col, float(rel_damp), L.ptr(U), L.ptr(ws), nws,
+                               L.ptr(flag), L.stream_of(H.device)))
     return U, flag
 
 
@@ -94,10 +119,11 @@ def gptq_quantize(W: torch.Tensor, U: torch.Tensor, q_type: int, block_size: int
     d_row, d_col = W.shape
     qweight, d, sq, dmin, zq, pk, wd = alloc_outputs(q_type, d_row, d_col, W.device, packed, wdeq_dtype)
     flags = torch.zeros(d_col // QK_K, 2, dtype=torch.int32, device=W.device) if search_flags else None
-    L.check(L.load().gq_gptq_quantize(
-        L.ptr(W), L.ptr(U), d_row, d_col, int(q_type), int(block_size), float(rmin), float(rdelta), int(nstep), int(mode),
-        L.ptr(qweight), L.ptr(d), L.ptr(sq), L.ptr(dmin), L.ptr(zq), L.ptr(pk), L.ptr(wd),
-        L.dtype_code(wdeq_dtype) if wdeq_dtype is not None else 0, L.ptr(flags), L.stream_of(W.device)))
+    with _span("gptq"):
+        L.check(L.load().gq_gptq_quantize(
+            L.ptr(W), L.ptr(U), d_row, d_col, int(q_type), int(block_size), float(rmin), float(rdelta), int(nstep), int(mode),
+            L.ptr(qweight), L.ptr(d), L.ptr(sq), L.ptr(dmin), L.ptr(zq), L.ptr(pk), L.ptr(wd),
+            L.dtype_code(wdeq_dtype) if wdeq_dtype is not None else 0, L.ptr(flags), L.stream_of(W.device)))
     return qweight, d, sq, dmin, zq, pk, wd, flags
 
 
@@ -109,10 +135,11 @@ def rtn_quantize(W: torch.Tensor, q_type: int, rmin: float = -1.0, rdelta: float
     assert W.is_contiguous() and W.dim() == 2
     d_row, d_col = W.shape
     qweight, d, sq, dmin, zq, pk, wd = alloc_outputs(q_type, d_row, d_col, W.device, packed, wdeq_dtype)
-    L.check(L.load().gq_rtn_quantize(
-        L.ptr(W), L.dtype_code(W.dtype), d_row, d_col, int(q_type), float(rmin), float(rdelta), int(nstep),
-        L.ptr(qweight), L.ptr(d), L.ptr(sq), L.ptr(dmin), L.ptr(zq), L.ptr(pk), L.ptr(wd),
-        L.dtype_code(wdeq_dtype) if wdeq_dtype is not None else 0, L.stream_of(W.device)))
+    with _span("rtn"):
+        L.check(L.load().gq_rtn_quantize(
+            L.ptr(W), L.dtype_code(W.dtype), d_row, d_col, int(q_type), float(rmin), float(rdelta), int(nstep),
+            L.ptr(qweight), L.ptr(d), L.ptr(sq), L.ptr(dmin), L.ptr(zq), L.ptr(pk), L.ptr(wd),
+            L.dtype_code(wdeq_dtype) if wdeq_dtype is not None else 0, L.stream_of(W.device)))
     return qweight, d, sq, dmin, zq, pk, wd
 
 

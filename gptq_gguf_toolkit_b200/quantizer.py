@@ -188,11 +188,10 @@ class Quantizer:
         q_type = quant_config.get(name.split(".")[-1], GGMLQuantizationType.Q6_K)
         kw = self.quantizer_kwargs
         w = module.weight.data
-        with self.timer.span("rtn"):
-            qweight, d, sq, dmin, zq, packed, wdeq = ops.rtn_quantize(
-                w.contiguous(), int(q_type), kw.get("rmin", -1.0), kw.get("rdelta", 0.1), kw.get("nstep", 20),
-                packed=self.save_packed, wdeq_dtype=w.dtype)
-            module.weight.data = wdeq
+        qweight, d, sq, dmin, zq, packed, wdeq = ops.rtn_quantize(
+            w.contiguous(), int(q_type), kw.get("rmin", -1.0), kw.get("rdelta", 0.1), kw.get("nstep", 20),
+            packed=self.save_packed, wdeq_dtype=w.dtype)
+        module.weight.data = wdeq
         self._emit(name, q_type, (qweight, d, sq, dmin, zq), packed)
 
     # -------------------------------------------------------------------------------------------
@@ -252,7 +251,7 @@ class Quantizer:
             dtype = hs[0].layer.weight.dtype
             # fp32 working copy of all members, stacked row-wise (gptq.py:138)
             rows = [h.d_row for h in hs]
-            with self.timer.span("prepare"):
+            with self.timer.span("prepare_host"):
                 W = torch.cat([h.layer.weight.data.float() for h in hs], dim=0).contiguous()
                 ops.pre_step(acc.H, W)                                         # gptq.py:134-141
                 masks = torch.stack([(w == 0).all(dim=0) for w in W.split(rows, dim=0)])
@@ -270,8 +269,7 @@ class Quantizer:
             for qt, idxs in by_type.items():
                 self._log(f"Quantizing {[names[i] for i in idxs]} with {GGMLQuantizationType(qt).name}.")
                 Wg = W if len(idxs) == len(hs) else torch.cat([W[offs[i]:offs[i + 1]] for i in idxs], 0).contiguous()
-                with self.timer.span("gptq"):
-                    outs = self._sharded_gptq(Wg, U, qt, dtype, rank, world)
+                outs = self._sharded_gptq(Wg, U, qt, dtype, rank, world)
                 qweight, d, sq, dmin, zq, packed, wdeq = outs
                 r0 = 0
                 for i in idxs:
@@ -343,6 +341,7 @@ class Quantizer:
     def quantize(self, quant_config: Dict[str, GGMLQuantizationType]) -> None:
         device = self.device or next(self.model.parameters()).device
         self._not_pd_flags = []
+        ops.set_timer(self.timer if self.timer.enabled else None)
         if self.save_dir is not None and _rank() == 0:
             os.makedirs(self.save_dir, exist_ok=True)
             self._saver = _AsyncSaver()
@@ -434,6 +433,7 @@ class Quantizer:
             self._saver = None
         if _dist_on():
             dist.barrier()
+        ops.set_timer(None)
 
     def non_invertible_modules(self) -> List[str]:
         """Modules whose Hessian was not positive definite (U fell back to identity, gptq.py:321-323). Synchronises."""
