@@ -1,0 +1,349 @@
+// hessian_tc.cu -- tensor-core Hessian accumulation  H <- beta*H + alpha * X^T X  for 16-bit activations
+// (replaces GPTQ.update's fp32 addmm_, quant/gptq/src/gptq.py:108-112 -- the FLOP giant of the whole run).
+//
+// bf16 x bf16 (and fp16 x fp16) products are exact in fp32, so feeding the 16-bit activations straight to
+// tcgen05.mma kind::f16 with fp32 TMEM accumulators gives the same class of result as the reference's fp32
+// GEMM of the widened inputs (only the summation order differs, which is unspecified in the reference too).
+//
+// Pipeline (one persistent CTA per SM, 256 threads, warp-specialised):
+//   transpose kernel : X (T x n) -> Xt (n x Tp), Tp = T rounded up to 64, zero padded  => both MMA operands K-major
+//   warp 0           : TMA producer, cp.async.bulk.tensor 2D, 128B swizzle, 4-stage mbarrier ring
+//                      stage = A tile 128 x 64 (16 KB) + B tile 256 x 64 (32 KB) of Xt
+//   warp 1           : one elected thread issues tcgen05.mma.cta_group::1.kind::f16, M128 N256 K16, accumulators
+//                      double-buffered in TMEM (2 x 256 columns) so the epilogue overlaps the next tile's MMAs
+//   warps 4-7        : epilogue: tcgen05.ld -> H = beta*H + alpha*acc, direct + mirrored store (H stays symmetric)
+// Only tiles that touch the upper triangle are computed (SYRK); strictly-lower elements come from the mirror.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int NTHREADS = 256;
+constexpr uint32_t TMEM_COLS = 512;
+
+struct Barriers {
+    uint64_t full[STAGES];
+    uint64_t empty[STAGES];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+};
+constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + sizeof(Barriers);
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a mis-programmed pipeline traps after ~2 s instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile (rows x 64 16-bit elements, 128 B per row, 8-row groups of 1024 B).
+// start address >> 4 | LBO (ignored for swizzled K-major) | SBO = 1024 B | version 1 (sm_100) | SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Upper-triangle tile list: tile (tm, tn) is needed iff its last column >= its first row, i.e. tn >= tm/2.
+__device__ __forceinline__ void tile_coords(int idx, int ntn, int &tm, int &tn) {
+    int m = 0;
+    while (true) {
+        const int cnt = ntn - (m >> 1);
+        if (idx < cnt) break;
+        idx -= cnt;
+        ++m;
+    }
+    tm = m;
+    tn = (m >> 1) + idx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// X (T x n) -> Xt (n x Tp), zero padded in t
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t *__restrict__ X, uint16_t *__restrict__ Xt,
+                                                          int T, int n, int Tp) {
+    __shared__ uint16_t tile[64][66];
+    const int t0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 x 4
+#pragma unroll
+    for (int r = ty; r < 64; r += 4) {
+        const int t = t0 + r;
+        tile[r][tx] = (t < T) ? X[(size_t)t * n + c0 + tx] : (uint16_t)0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 64; r += 4) Xt[(size_t)(c0 + r) * Tp + t0 + tx] = tile[tx][r];
+}
+
+// ---------------------------------------------------------------------------------------------
+// persistent SYRK kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1)
+hessian_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, float *H,
+                  int n, int nkb, int ntiles, float alpha, float beta, uint32_t idesc) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    Barriers &bar = *reinterpret_cast<Barriers *>(smem + (size_t)STAGES * STAGE_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntn = n / BN;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&bar.full[s], 1); mbar_init(&bar.empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&bar.tmem_full[b], 1); mbar_init(&bar.tmem_empty[b], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bar.tmem_base)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bar.tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0, phase = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                int tm, tn;
+                tile_coords(t, ntn, tm, tn);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&bar.empty[stage], phase ^ 1);
+                    uint8_t *a = smem + (size_t)stage * STAGE_BYTES;
+                    mbar_expect_tx(&bar.full[stage], STAGE_BYTES);
+                    tma_load_2d(a, &map_a, &bar.full[stage], kb * BK, tm * BM);
+                    tma_load_2d(a + A_BYTES, &map_b, &bar.full[stage], kb * BK, tn * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int stage = 0, phase = 0, it = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&bar.tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * BN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&bar.full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                    const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)   // +32 B per K step inside the 128 B swizzle span
+                        tc_mma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    tc_commit(&bar.empty[stage]);            // frees the smem stage when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&bar.tmem_full[buf]);              // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> H =====
+        const int q = warp & 3;     // TMEM lane quadrant of this warp
+        int it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            int tm, tn;
+            tile_coords(t, ntn, tm, tn);
+            const int buf = it & 1;
+            mbar_wait(&bar.tmem_full[buf], (it >> 1) & 1);
+            tc_fence_after();
+            const int i = tm * BM + q * 32 + lane;            // global row of this thread
+            const int i_lo = tm * BM + q * 32, i_hi = i_lo + 31;
+            float *hrow = H + (size_t)i * n;
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                const int j0 = tn * BN + ch * 32;
+                if (j0 + 31 < i_lo) continue;                 // chunk entirely below the diagonal: mirrored from elsewhere
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + ch * 32), v);
+                const bool all_upper = (j0 >= i_hi);          // every (i, j) of this warp's chunk has j >= i
+                if (all_upper) {
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (beta != 0.0f) h = *reinterpret_cast<const float4 *>(hrow + j0 + 4 * c4);
+                        float4 o;
+                        o.x = __fmaf_rn(alpha, __uint_as_float(v[4 * c4 + 0]), __fmul_rn(beta, h.x));
+                        o.y = __fmaf_rn(alpha, __uint_as_float(v[4 * c4 + 1]), __fmul_rn(beta, h.y));
+                        o.z = __fmaf_rn(alpha, __uint_as_float(v[4 * c4 + 2]), __fmul_rn(beta, h.z));
+                        o.w = __fmaf_rn(alpha, __uint_as_float(v[4 * c4 + 3]), __fmul_rn(beta, h.w));
+                        *reinterpret_cast<float4 *>(hrow + j0 + 4 * c4) = o;
+                        v[4 * c4 + 0] = __float_as_uint(o.x); v[4 * c4 + 1] = __float_as_uint(o.y);
+                        v[4 * c4 + 2] = __float_as_uint(o.z); v[4 * c4 + 3] = __float_as_uint(o.w);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)             // mirror: lanes write consecutive addresses
+                        if (j0 + c != i) H[(size_t)(j0 + c) * n + i] = __uint_as_float(v[c]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int j = j0 + c;
+                        if (j >= i) {
+                            const float h = (beta != 0.0f) ? hrow[j] : 0.0f;
+                            const float o = __fmaf_rn(alpha, __uint_as_float(v[c]), __fmul_rn(beta, h));
+                            hrow[j] = o;
+                            if (j != i) H[(size_t)j * n + i] = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar.tmem_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+bool make_map(CUtensorMap *m, void *base, int dtype, uint64_t rows, uint64_t cols_padded, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {cols_padded, rows};
+    cuuint64_t strides[1] = {cols_padded * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = dtype == GQ_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    return fn(m, dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace
+
+size_t gq_hessian_tc_workspace_bytes(long n_tok, int d_col) {
+    const long Tp = (n_tok + BK - 1) / BK * BK;
+    return (size_t)d_col * (size_t)Tp * 2 + 1024;
+}
+
+bool gq_hessian_tc_supported(long n_tok, int d_col, int x_dtype) {
+    return (x_dtype == GQ_BF16 || x_dtype == GQ_F16) && d_col % BN == 0 && n_tok > 0;
+}
+
+int gq_hessian_tc(float *H, const void *X, long n_tok, int d_col, int x_dtype, float beta, float alpha, void *workspace,
+                  size_t ws_bytes, cudaStream_t st) {
+    if (ws_bytes < gq_hessian_tc_workspace_bytes(n_tok, d_col) || workspace == nullptr) {
+        gq_set_error("gq_hessian_update: workspace %zu < %zu bytes", ws_bytes, gq_hessian_tc_workspace_bytes(n_tok, d_col));
+        return GQ_ERR_WORKSPACE;
+    }
+    const int n = d_col, T = (int)n_tok;
+    const int Tp = (T + BK - 1) / BK * BK;
+    uint16_t *Xt = reinterpret_cast<uint16_t *>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    {
+        dim3 grid(Tp / 64, n / 64);
+        transpose16_kernel<<<grid, 256, 0, st>>>((const uint16_t *)X, Xt, T, n, Tp);
+        gq_count_launches(1);
+    }
+    CUtensorMap map_a, map_b;
+    if (!make_map(&map_a, Xt, x_dtype, (uint64_t)n, (uint64_t)Tp, BM) || !make_map(&map_b, Xt, x_dtype, (uint64_t)n, (uint64_t)Tp, BN)) {
+        gq_set_error("gq_hessian_update: cuTensorMapEncodeTiled failed");
+        return GQ_ERR_CUDA;
+    }
+    const int ntm = n / BM, ntn = n / BN;
+    int ntiles = 0;
+    for (int m = 0; m < ntm; ++m) ntiles += ntn - (m >> 1);
+    const uint32_t fmt = x_dtype == GQ_BF16 ? 1u : 0u;
+    // kind::f16 instruction descriptor: D = F32, A/B = fmt, both K-major, N = 256, M = 128
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    GQ_CHECK_CUDA(cudaFuncSetAttribute(hessian_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    const int grid = ntiles < num_sms() ? ntiles : num_sms();
+    hessian_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(map_a, map_b, H, n, Tp / BK, ntiles, alpha, beta, idesc);
+    gq_count_launches(1);
+    GQ_CHECK_CUDA(cudaGetLastError());
+    return GQ_OK;
+}

@@ -160,18 +160,26 @@ sg::Args gemm_args(const float *A, long a_rs, long a_cs, const float *B, long b_
 }  // namespace
 
 // =============================================================================================
+// tcgen05 path (hessian_tc.cu)
+size_t gq_hessian_tc_workspace_bytes(long n_tok, int d_col);
+bool gq_hessian_tc_supported(long n_tok, int d_col, int x_dtype);
+int gq_hessian_tc(float *H, const void *X, long n_tok, int d_col, int x_dtype, float beta, float alpha, void *workspace,
+                  size_t ws_bytes, cudaStream_t st);
+
 extern "C" size_t gq_hessian_workspace_bytes(long n_tok, int d_col, int x_dtype) {
-    (void)n_tok; (void)d_col; (void)x_dtype;
-    return 0;
+    return gq_hessian_tc_supported(n_tok, d_col, x_dtype) ? gq_hessian_tc_workspace_bytes(n_tok, d_col) : 0;
 }
 
 extern "C" int gq_hessian_update(float *H, const void *X, long n_tok, int d_col, int x_dtype, float beta, float alpha,
                                  void *workspace, size_t ws_bytes, gq_stream_t stream) {
-    (void)workspace; (void)ws_bytes;
     GQ_REQUIRE(H && X, "gq_hessian_update: null pointer");
     GQ_REQUIRE(d_col > 0 && d_col % 128 == 0, "gq_hessian_update: d_col=%d must be a positive multiple of 128", d_col);
     GQ_REQUIRE(n_tok > 0 && n_tok < (1L << 31), "gq_hessian_update: bad n_tok %ld", n_tok);
     GQ_REQUIRE(x_dtype >= GQ_F32 && x_dtype <= GQ_BF16, "gq_hessian_update: bad x_dtype %d", x_dtype);
+    GQ_REQUIRE(((uintptr_t)H | (uintptr_t)X) % 16 == 0, "gq_hessian_update: H and X must be 16-byte aligned");
+    if (gq_hessian_tc_supported(n_tok, d_col, x_dtype))     // 16-bit activations: tcgen05 tensor cores
+        return gq_hessian_tc(H, X, n_tok, d_col, x_dtype, beta, alpha, workspace, ws_bytes, (cudaStream_t)stream);
+    // fp32 activations (or d_col not a multiple of 256): fp32 SIMT tiles
     sg::Args a;
     a.A = X; a.B = X; a.C = H;
     a.a_rs = 1; a.a_cs = d_col;      // A(m,k) = X[k][m]

@@ -180,10 +180,25 @@ def test_pack_dequant_golden_and_gguf_py(ops, golden_dir, tname):
 # ------------------------------------------------------------------------------------------------
 # Hessian and Cholesky chain (floating point: tolerance stated in each test)
 # ------------------------------------------------------------------------------------------------
+def test_hessian_tensor_core_path_large(ops):
+    """tcgen05 SYRK at a Llama-sized d_col: several tiles per CTA, both TMEM accumulator buffers, k tail padding."""
+    torch.manual_seed(3)
+    d_col, T = 4096, 4096 + 40
+    x = (torch.randn(T, d_col, device="cuda") * torch.linspace(0.1, 3.0, d_col, device="cuda")).to(torch.bfloat16)
+    H = torch.randn(d_col, d_col, device="cuda")
+    H = (H + H.T).contiguous()
+    ref = 0.25 * H.double() + 0.5 * (x.double().T @ x.double())
+    ops.hessian_update(H, x, 0.25, 0.5)
+    torch.cuda.synchronize()
+    # exact bf16 products, fp32 accumulation over 4136 tokens: 5e-5 of the matrix scale
+    assert (H.double() - ref).abs().max() <= 5e-5 * ref.abs().max()
+    assert torch.equal(H, H.T)
+
+
+@pytest.mark.parametrize("d_col", [384, 512, 1280])
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
-def test_hessian_update(ops, dt):
+def test_hessian_update(ops, dt, d_col):
     torch.manual_seed(0)
-    d_col = 384
     H = torch.zeros(d_col, d_col, device="cuda")
     ref = torch.zeros(d_col, d_col, dtype=torch.float64)
     n = 0
