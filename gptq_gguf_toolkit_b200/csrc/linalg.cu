@@ -77,8 +77,8 @@ __global__ void reverse_copy_kernel(const float *__restrict__ H, float *A, int n
 
 // Factor the (128 x 128) diagonal block at A[k0:k0+128, k0:k0+128] in shared memory: L_kk (written back to A)
 // and inv(L_kk) (written to Binv, the level-0 blocks of the triangular inverse; upper part zeroed).
-constexpr int DT = 512;
-struct DiagSmem { float L[NB][NB + 1]; float X[NB][NB + 1]; };
+constexpr int DT = 1024;
+struct DiagSmem { float L[NB][NB + 1]; float X[NB][NB + 1]; float d[NB]; };
 __global__ void __launch_bounds__(DT) chol_diag_kernel(float *A, float *Binv, long ld, int k0, int *not_pd) {
     extern __shared__ __align__(16) uint8_t raw[];
     DiagSmem &s = *reinterpret_cast<DiagSmem *>(raw);
@@ -89,40 +89,51 @@ __global__ void __launch_bounds__(DT) chol_diag_kernel(float *A, float *Binv, lo
         const int i = id >> 7, j = id & 127;
         s.L[i][j] = (j <= i) ? Ab[(size_t)i * ld + j] : 0.0f;
     }
+    for (int id = tid; id < NB * NB; id += DT) s.X[id >> 7][id & 127] = ((id >> 7) == (id & 127)) ? 1.0f : 0.0f;
     __syncthreads();
+    // Column sweep, two barriers per column.  Right-looking Cholesky of L fused with the forward elimination
+    // that turns X = I into inv(L):  X_j /= l_jj, then X_i -= l_ij X_j for i > j.
     for (int j = 0; j < NB; ++j) {
+        __syncthreads();                                   // trailing updates of column j-1 are visible
+        float piv = s.L[j][j];                             // stays un-rooted in smem; the root goes to s.d[j]
+        const bool bad = !(piv > 0.0f) || !isfinite(piv);
+        if (bad) piv = 1.0f;
+        const float dj = __fsqrt_rn(piv), inv = __frcp_rn(dj);
         if (tid == 0) {
-            float piv = s.L[j][j];
-            if (!(piv > 0.0f) || !isfinite(piv)) { *not_pd = 1; piv = 1.0f; }
-            s.L[j][j] = __fsqrt_rn(piv);
+            s.d[j] = dj;
+            if (bad) *not_pd = 1;
         }
-        __syncthreads();
-        const float inv = __frcp_rn(s.L[j][j]);
         for (int i = j + 1 + tid; i < NB; i += DT) s.L[i][j] = __fmul_rn(s.L[i][j], inv);
+        for (int c = tid; c <= j; c += DT) s.X[j][c] = __fmul_rn(s.X[j][c], inv);
         __syncthreads();
-        const int m = NB - 1 - j;   // trailing size
-        for (int id = tid; id < m * m; id += DT) {
-            const int i = j + 1 + id / m, k = j + 1 + id % m;
-            if (k <= i) s.L[i][k] = __fmaf_rn(-s.L[i][j], s.L[k][j], s.L[i][k]);
-        }
-        __syncthreads();
-    }
-    // X = inv(L): thread c owns column c, forward substitution in lock step over (i, k)
-    if (tid < NB) {
-        const int c = tid;
-        for (int i = 0; i < NB; ++i) {
-            float acc = (i == c) ? 1.0f : 0.0f;
-            for (int k = 0; k < i; ++k) {
-                const float xk = (k >= c) ? s.X[k][c] : 0.0f;
-                acc = __fmaf_rn(-s.L[i][k], xk, acc);
+        // Rows below j: columns c <= j belong to X (X_i -= l_ij X_j), columns j < c <= i to L (L_ic -= l_ij l_cj).
+        // A thread owns one column and every RG-th row; its column factor is loaded once, and the rows are
+        // processed four at a time with all loads ahead of the stores (the chain is latency bound otherwise).
+        {
+            constexpr int RG = DT / NB;
+            const int c = tid & (NB - 1), rg = tid >> 7;
+            const bool isX = (c <= j);
+            const float colv = isX ? s.X[j][c] : s.L[c][j];
+            float (*T)[NB + 1] = isX ? s.X : s.L;
+            for (int i0 = j + 1 + rg; i0 < NB; i0 += 4 * RG) {
+                float lij[4], t[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * RG;
+                    if (i < NB) { lij[u] = s.L[i][j]; t[u] = T[i][c]; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * RG;
+                    if (i < NB && (isX || c <= i)) T[i][c] = __fmaf_rn(-lij[u], colv, t[u]);
+                }
             }
-            s.X[i][c] = (i >= c) ? __fdiv_rn(acc, s.L[i][i]) : 0.0f;
         }
     }
     __syncthreads();
     for (int id = tid; id < NB * NB; id += DT) {
         const int i = id >> 7, j = id & 127;
-        if (j <= i) Ab[(size_t)i * ld + j] = s.L[i][j];
+        if (j <= i) Ab[(size_t)i * ld + j] = (i == j) ? s.d[i] : s.L[i][j];
         Bb[(size_t)i * ld + j] = s.X[i][j];
     }
 }

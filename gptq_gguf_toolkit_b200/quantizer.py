@@ -92,7 +92,8 @@ class _AsyncSaver:
                 return
             obj, path, ready = item
             try:
-                ready.synchronize()     # the D2H copies were enqueued before this event
+                if ready is not None:
+                    ready.synchronize()     # the D2H copies were enqueued before this event
                 os.makedirs(os.path.dirname(path), exist_ok=True)
                 torch.save(obj, path)
             except BaseException as e:  # noqa: BLE001
@@ -160,7 +161,7 @@ class Quantizer:
         qweight, d, sq, dmin, zq = five
 
         def host(t):   # pinned destination => the copy is truly asynchronous (torch caches pinned blocks)
-            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=t.is_cuda)
             buf.copy_(t, non_blocking=True)
             return buf
 
@@ -175,8 +176,10 @@ class Quantizer:
             }
             if self.save_packed and packed is not None:
                 obj["packed"] = host(packed)
-            ready = torch.cuda.Event()
-            ready.record()
+            ready = None
+            if qweight.is_cuda:
+                ready = torch.cuda.Event()
+                ready.record()
         if self.keep_results:
             self.results[name] = obj
         if self.save_dir is not None:

@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Micro-timings of the individual libgq ops at Llama-3-8B layer shapes (CUDA events, 1 GPU).
+    python profiles/micro.py [prepare] [gptq] [hessian] [rtn]
+"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from gptq_gguf_toolkit_b200 import ops  # noqa: E402
+
+
+def timed(fn, warm=1, it=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(it):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return min(ts), sum(ts) / len(ts)
+
+
+def spd(n, dev="cuda"):
+    x = torch.randn(2 * n, n, device=dev)
+    H = (x.T @ x) / n
+    return H
+
+
+def main():
+    what = set(sys.argv[1:]) or {"prepare", "gptq", "hessian", "rtn"}
+    torch.manual_seed(0)
+    if "prepare" in what:
+        for n in (4096, 14336):
+            H0 = spd(n)
+            W = torch.randn(256, n, device="cuda")
+            l0 = ops.launch_count()
+            mn, av = timed(lambda: ops.prepare(H0.clone(), W, 0.01), warm=1, it=2)
+            print(f"prepare n={n}: {mn:.2f} ms (avg {av:.2f}), launches/call {(ops.launch_count() - l0) // 3}", flush=True)
+    if "hessian" in what:
+        for n, T in ((4096, 16384), (14336, 16384)):
+            X = torch.randn(T, n, device="cuda").to(torch.bfloat16)
+            H = torch.zeros(n, n, device="cuda")
+            mn, av = timed(lambda: ops.hessian_update(H, X, 0.5, 0.5), warm=1, it=3)
+            print(f"hessian n={n} T={T}: {mn:.3f} ms  -> {2 * T * n * n / 2 / mn / 1e9:.0f} TFLOP/s (upper-triangle flops)", flush=True)
+    if "gptq" in what:
+        for rows, n in ((6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336)):
+            U = torch.triu(torch.randn(n, n, device="cuda") * 0.01) + torch.eye(n, device="cuda")
+            W0 = torch.randn(rows, n, device="cuda") * 0.02
+            mn, av = timed(lambda: ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16), warm=1, it=2)
+            fl = rows * n * (n - 128)
+            print(f"gptq {rows}x{n}: {mn:.2f} ms -> rank-k {fl / mn / 1e9:.1f} TFLOP/s", flush=True)
+    if "rtn" in what:
+        W = torch.randn(128256, 4096, device="cuda").to(torch.bfloat16)
+        mn, av = timed(lambda: ops.rtn_quantize(W, 12, wdeq_dtype=torch.bfloat16), warm=1, it=2)
+        print(f"rtn 128256x4096: {mn:.2f} ms", flush=True)
+
+
+if __name__ == "__main__":
+    t0 = time.time()
+    main()
+    print(f"wall {time.time() - t0:.1f} s")
