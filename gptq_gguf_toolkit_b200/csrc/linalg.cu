@@ -9,6 +9,9 @@
 // the reversed matrix plus one blocked triangular inverse (2n^3/3 flops), then a reversed copy.
 // The triangular inverse is a log-depth pairwise merge  inv([[A,0],[C,B]]) = [[Ai,0],[-Bi C Ai, Bi]],
 // whose work is all GEMM (zero tiles of the triangular factors are skipped).
+#include <cstdlib>
+
+#include "gemm_tf32.cuh"
 #include "sgemm.cuh"
 
 namespace {
@@ -79,7 +82,7 @@ __global__ void reverse_copy_kernel(const float *__restrict__ H, float *A, int n
 // and inv(L_kk) (written to Binv, the level-0 blocks of the triangular inverse; upper part zeroed).
 constexpr int DT = 1024;
 struct DiagSmem { float L[NB][NB + 1]; float X[NB][NB + 1]; float d[NB]; };
-__global__ void __launch_bounds__(DT) chol_diag_kernel(float *A, float *Binv, long ld, int k0, int *not_pd) {
+__global__ void __launch_bounds__(DT) chol_diag_kernel(float *A, float *Binv, float *BinvT, long ld, int k0, int *not_pd) {
     extern __shared__ __align__(16) uint8_t raw[];
     DiagSmem &s = *reinterpret_cast<DiagSmem *>(raw);
     const int tid = threadIdx.x;
@@ -135,7 +138,20 @@ __global__ void __launch_bounds__(DT) chol_diag_kernel(float *A, float *Binv, lo
         const int i = id >> 7, j = id & 127;
         if (j <= i) Ab[(size_t)i * ld + j] = (i == j) ? s.d[i] : s.L[i][j];
         Bb[(size_t)i * ld + j] = s.X[i][j];
+        if (BinvT != nullptr) BinvT[(size_t)(k0 + i) * ld + k0 + j] = s.X[j][i];   // inv(L_kk)^T, upper triangular
     }
+}
+
+// dst[b][c][r] = src[b][r][c]  (rows x cols block of a strided matrix -> cols x rows block of another), 32x32 tiles
+__global__ void __launch_bounds__(256) transpose_block_kernel(const float *__restrict__ src, long ld_src, long bs_src,
+                                                              float *__restrict__ dst, long ld_dst, long bs_dst, int rows, int cols) {
+    __shared__ float t[32][33];
+    const float *S = src + (long)blockIdx.z * bs_src;
+    float *D = dst + (long)blockIdx.z * bs_dst;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) t[r][tx] = S[(long)(r0 + r) * ld_src + c0 + tx];
+    __syncthreads();
+    for (int c = ty; c < 32; c += 8) D[(long)(c0 + c) * ld_dst + r0 + tx] = t[tx][c];
 }
 
 // U[i][j] = Linv[n-1-i][n-1-j] for j >= i, 0 below; identity if the factorisation failed (gptq.py:321-323).
@@ -211,16 +227,26 @@ extern "C" int gq_pre_step(float *H, float *W, int d_row, int d_col, gq_stream_t
     return GQ_OK;
 }
 
-// workspace: A (n*n) | Linv (n*n) | nz (n ints) | flag (1 int, padded)
+// workspace: A (n*n) | Linv (n*n) | Linv^T (n*n) | nz (n ints) + flag | 3xTF32 operand splits
+namespace {
+size_t split_ws_bytes(size_t n) { return (size_t)(1.25 * (double)n * (double)n) * sizeof(float) + (n * 512 + 1024) * sizeof(float) + 8192; }
+bool prepare_use_simt() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("GQ_PREPARE_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+}  // namespace
+
 extern "C" size_t gq_prepare_workspace_bytes(int d_col) {
     const size_t n = (size_t)d_col;
-    return 2 * n * n * sizeof(float) + (n + 64) * sizeof(int);
+    return 3 * n * n * sizeof(float) + (n + 64) * sizeof(int) + 1024 + split_ws_bytes(n);
 }
 
 extern "C" int gq_prepare(float *H, const float *W, int d_row, int d_col, float rel_damp, float *U_out, void *workspace,
                           size_t ws_bytes, int *not_pd_flag, gq_stream_t stream) {
     GQ_REQUIRE(H && W && U_out && workspace, "gq_prepare: null pointer");
     GQ_REQUIRE(d_row > 0 && d_col > 0 && d_col % NB == 0, "gq_prepare: d_col=%d must be a positive multiple of 128", d_col);
+    GQ_REQUIRE(((uintptr_t)H | (uintptr_t)U_out | (uintptr_t)workspace) % 16 == 0, "gq_prepare: H, U_out, workspace must be 16-byte aligned");
     if (ws_bytes < gq_prepare_workspace_bytes(d_col)) {
         gq_set_error("gq_prepare: workspace %zu < %zu bytes", ws_bytes, gq_prepare_workspace_bytes(d_col));
         return GQ_ERR_WORKSPACE;
@@ -228,10 +254,14 @@ extern "C" int gq_prepare(float *H, const float *W, int d_row, int d_col, float 
     cudaStream_t st = (cudaStream_t)stream;
     const int n = d_col;
     const long ld = n;
+    const bool simt = prepare_use_simt();
     float *A = (float *)workspace;
     float *Li = A + (size_t)n * n;
-    int *nz = (int *)(Li + (size_t)n * n);
+    float *LiT = Li + (size_t)n * n;
+    int *nz = (int *)(LiT + (size_t)n * n);
     int *flag = nz + n;
+    void *sws = (void *)(((uintptr_t)(nz + n + 64) + 1023) & ~(uintptr_t)1023);
+    const size_t sws_bytes = split_ws_bytes((size_t)n);
 
     // --- masks + damping (gptq.py:308-316) ---
     GQ_CHECK_CUDA(cudaMemsetAsync(nz, 0, (size_t)(n + 64) * sizeof(int), st));
@@ -244,55 +274,103 @@ extern "C" int gq_prepare(float *H, const float *W, int d_row, int d_col, float 
     damp_kernel<<<1, 1024, 0, st>>>(H, n, rel_damp);
     gq_count_launches(3);
 
-    // --- L = chol(J H J), level-0 blocks of inv(L) ---
+    // --- L = chol(J H J); inv(L_kk) and its transpose for every diagonal block ---
     reverse_copy_kernel<<<ew_grid((long)n * n), 256, 0, st>>>(H, A, n);
     gq_count_launches(1);
     GQ_CHECK_CUDA(cudaMemsetAsync(Li, 0, (size_t)n * n * sizeof(float), st));
+    if (!simt) GQ_CHECK_CUDA(cudaMemsetAsync(LiT, 0, (size_t)n * n * sizeof(float), st));
     GQ_CHECK_CUDA(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DiagSmem)));
+    auto tc_gemm = [&](const float *Ap, const float *Bp, float *Cp, int M, int N, int K, int batch, long ab, long bb, long cb,
+                       float alpha, float beta, int tile_mode, int k_mode, bool same) {
+        tg::GemmArgs g;
+        g.A = Ap; g.lda = ld; g.a_batch = ab; g.B = Bp; g.ldb = ld; g.b_batch = bb; g.C = Cp; g.ldc = ld; g.c_batch = cb;
+        g.M = M; g.N = N; g.K = K; g.batch = batch; g.alpha = alpha; g.beta = beta; g.tile_mode = tile_mode; g.k_mode = k_mode;
+        g.same_ab = same;
+        return tg::gemm_tf32x3_nt(g, sws, sws_bytes, st);
+    };
     for (int k0 = 0; k0 < n; k0 += NB) {
-        chol_diag_kernel<<<1, DT, sizeof(DiagSmem), st>>>(A, Li, ld, k0, flag);
+        chol_diag_kernel<<<1, DT, sizeof(DiagSmem), st>>>(A, Li, simt ? nullptr : LiT, ld, k0, flag);
         gq_count_launches(1);
         const int rem = n - k0 - NB;
         if (rem > 0) {
             float *P = A + (size_t)(k0 + NB) * ld + k0;          // panel (rem x 128)
-            const float *Lkk_inv = Li + (size_t)k0 * ld + k0;     // inv(L_kk)
-            // P <- P * inv(L_kk)^T   : A(m,k) = P[m][k], B(k,n) = Lkk_inv[n][k]; B lower-tri => k <= n, one tile: full
-            int rc = sg::launch(gemm_args(P, ld, 1, Lkk_inv, 1, ld, P, ld, rem, NB, NB, 1.0f, 0.0f, sg::TM_FULL, sg::KM_FULL), 1, st);
-            if (rc) return rc;
-            // trailing lower triangle:  T <- T - P P^T
-            float *T = A + (size_t)(k0 + NB) * ld + (k0 + NB);
-            rc = sg::launch(gemm_args(P, ld, 1, P, 1, ld, T, ld, rem, rem, NB, -1.0f, 1.0f, sg::TM_LOWER, sg::KM_FULL), 1, st);
+            const float *Lkk_inv = Li + (size_t)k0 * ld + k0;     // inv(L_kk), row-major lower
+            float *T = A + (size_t)(k0 + NB) * ld + (k0 + NB);    // trailing matrix
+            int rc;
+            if (simt) {
+                // P <- P * inv(L_kk)^T : A(m,k) = P[m][k], B(k,n) = Lkk_inv[n][k]
+                rc = sg::launch(gemm_args(P, ld, 1, Lkk_inv, 1, ld, P, ld, rem, NB, NB, 1.0f, 0.0f, sg::TM_FULL, sg::KM_FULL), 1, st);
+                if (rc) return rc;
+                rc = sg::launch(gemm_args(P, ld, 1, P, 1, ld, T, ld, rem, rem, NB, -1.0f, 1.0f, sg::TM_LOWER, sg::KM_FULL), 1, st);
+            } else {
+                // both GEMMs are NT (K-contiguous operands); operands are copied (split) before C is written => in place is safe
+                rc = tc_gemm(P, Lkk_inv, P, rem, NB, NB, 1, 0, 0, 0, 1.0f, 0.0f, tg::TM_FULL, tg::KM_FULL, false);
+                if (rc) return rc;
+                rc = tc_gemm(P, P, T, rem, rem, NB, 1, 0, 0, 0, -1.0f, 1.0f, tg::TM_LOWER, tg::KM_FULL, true);   // T -= P P^T
+            }
             if (rc) return rc;
         }
     }
 
-    // --- inv(L) by pairwise merging of diagonal blocks; U_out is the scratch for C * Ai ---
-    // blocks are described by their boundaries; every level merges neighbours (sizes may differ at the tail)
+    // --- X = inv(L) by pairwise merging of diagonal blocks:  X21 = -X22 * L21 * X11.  U_out is the scratch. ---
+    // Tensor path keeps Y = X^T as well so that every product is NT:
+    //   T^T[a][b] = sum_k Y11[a][k] L21[b][k]   (Y11 upper: k >= a)      X21[b][a] = -sum_k X22[b][k] T^T[a][k]   (X22 lower: k <= b)
     {
         int nblk = n / NB;
         int *start = new int[nblk + 1];
         for (int i = 0; i <= nblk; ++i) start[i] = i * NB;
-        while (nblk > 1) {
+        int rc = GQ_OK;
+        while (nblk > 1 && rc == GQ_OK) {
             int out = 0;
-            for (int b = 0; b + 1 < nblk; b += 2) {
-                const int r1 = start[b], r2 = start[b + 1], r3 = start[b + 2];
-                const int s1 = r2 - r1, s2 = r3 - r2;
-                const float *C = A + (size_t)r2 * ld + r1;      // L[rows2, cols1]   (s2 x s1)
-                const float *Ai = Li + (size_t)r1 * ld + r1;    // inv block 1       (s1 x s1, lower)
-                const float *Bi = Li + (size_t)r2 * ld + r2;    // inv block 2       (s2 x s2, lower)
-                float *Tm = U_out + (size_t)r2 * ld + r1;       // scratch           (s2 x s1)
-                float *O = Li + (size_t)r2 * ld + r1;           // result            (s2 x s1)
-                int rc = sg::launch(gemm_args(C, ld, 1, Ai, ld, 1, Tm, ld, s2, s1, s1, 1.0f, 0.0f, sg::TM_FULL, sg::KM_FROM_N), 1, st);
-                if (rc) { delete[] start; return rc; }
-                rc = sg::launch(gemm_args(Bi, ld, 1, Tm, ld, 1, O, ld, s2, s1, s2, -1.0f, 0.0f, sg::TM_FULL, sg::KM_TO_M), 1, st);
-                if (rc) { delete[] start; return rc; }
-                start[out++] = r1;
+            if (simt) {
+                for (int b = 0; b + 1 < nblk && rc == GQ_OK; b += 2) {
+                    const int r1 = start[b], r2 = start[b + 1], r3 = start[b + 2];
+                    const int s1 = r2 - r1, s2 = r3 - r2;
+                    const float *C = A + (size_t)r2 * ld + r1;
+                    const float *Ai = Li + (size_t)r1 * ld + r1;
+                    const float *Bi = Li + (size_t)r2 * ld + r2;
+                    float *Tm = U_out + (size_t)r2 * ld + r1;
+                    float *O = Li + (size_t)r2 * ld + r1;
+                    rc = sg::launch(gemm_args(C, ld, 1, Ai, ld, 1, Tm, ld, s2, s1, s1, 1.0f, 0.0f, sg::TM_FULL, sg::KM_FROM_N), 1, st);
+                    if (rc == GQ_OK)
+                        rc = sg::launch(gemm_args(Bi, ld, 1, Tm, ld, 1, O, ld, s2, s1, s2, -1.0f, 0.0f, sg::TM_FULL, sg::KM_TO_M), 1, st);
+                }
+            } else {
+                // uniform pairs of this level go out as one batched launch, an odd-sized tail pair separately
+                const int npairs = nblk / 2;
+                int b = 0;
+                while (b < npairs && rc == GQ_OK) {
+                    const int r1 = start[2 * b], r2 = start[2 * b + 1], r3 = start[2 * b + 2];
+                    const int s1 = r2 - r1, s2 = r3 - r2;
+                    int cnt = 1;
+                    while (b + cnt < npairs && start[2 * (b + cnt) + 1] - start[2 * (b + cnt)] == s1 &&
+                           start[2 * (b + cnt) + 2] - start[2 * (b + cnt) + 1] == s2)
+                        ++cnt;
+                    const long bstride = (long)(s1 + s2) * (ld + 1);          // next pair sits one (s1+s2) block down the diagonal
+                    const float *L21 = A + (size_t)r2 * ld + r1;             // (s2 x s1)
+                    const float *Y11 = LiT + (size_t)r1 * ld + r1;           // (s1 x s1) upper
+                    const float *X22 = Li + (size_t)r2 * ld + r2;            // (s2 x s2) lower
+                    float *Tt = U_out + (size_t)r1 * ld + r2;                // (s1 x s2) scratch
+                    float *X21 = Li + (size_t)r2 * ld + r1;                  // (s2 x s1)
+                    float *Y12 = LiT + (size_t)r1 * ld + r2;                 // (s1 x s2)
+                    rc = tc_gemm(Y11, L21, Tt, s1, s2, s1, cnt, bstride, bstride, bstride, 1.0f, 0.0f, tg::TM_FULL, tg::KM_FROM_M, false);
+                    if (rc == GQ_OK)
+                        rc = tc_gemm(X22, Tt, X21, s2, s1, s2, cnt, bstride, bstride, bstride, -1.0f, 0.0f, tg::TM_FULL, tg::KM_TO_M, false);
+                    if (rc == GQ_OK) {
+                        dim3 g(s1 / 32, s2 / 32, cnt);
+                        transpose_block_kernel<<<g, 256, 0, st>>>(X21, ld, bstride, Y12, ld, bstride, s2, s1);
+                        gq_count_launches(1);
+                    }
+                    b += cnt;
+                }
             }
+            for (int b = 0; b + 1 < nblk; b += 2) start[out++] = start[b];
             if (nblk & 1) start[out++] = start[nblk - 1];
             start[out] = n;
             nblk = out;
         }
         delete[] start;
+        if (rc != GQ_OK) return rc;
     }
 
     finish_u_kernel<<<ew_grid((long)n * n), 256, 0, st>>>(Li, U_out, n, flag);
