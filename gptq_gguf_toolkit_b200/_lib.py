@@ -37,7 +37,10 @@ SIGNATURES = {
     "gq_pre_step": (_i, [_vp, _vp, _i, _i, _vp]),
     "gq_prepare_workspace_bytes": (_sz, [_i]),
     "gq_prepare": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp, _sz, _vp, _vp]),
-    "gq_gptq_quantize": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "gq_gptq_workspace_bytes": (_sz, [_i, _i, _i]),
+    "gq_gptq_quantize": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "gq_profile_enable": (None, [_i]),
+    "gq_profile_read": (_i, [C.POINTER(_f), C.POINTER(_i)]),
     "gq_rtn_quantize": (_i, [_vp, _i, _i, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "gq_get_scale_and_zero": (_i, [_vp, _l, _i, _i, _d, _d, _i, _vp, _vp, _l, _vp, _vp, _l, _vp, _vp]),
     "gq_dequantize": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp]),

@@ -37,6 +37,8 @@ struct KParams {
     float *C;
     long ldc, c_batch;
     int M, N, nkb, batch, tiles_per_batch, ntn;
+    int a_row0, b_row0, a_kb0, b_kb0;      // offsets of the operands inside the arrays the tensor maps cover
+    int m_valid;                           // rows m >= m_valid of C are neither read nor written (ragged M)
     float alpha, beta;
     int tile_mode, k_mode;
     uint32_t idesc;
@@ -116,15 +118,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
                 int b, tm, tn, kb0, kb1;
                 decode_tile(p, t, b, tm, tn, kb0, kb1);
-                const int arow = b * p.M + tm * BM, brow = b * p.N + tn * BN;
+                const int arow = p.a_row0 + b * p.M + tm * BM, brow = p.b_row0 + b * p.N + tn * BN;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&bar.empty[stage], phase ^ 1);
                     uint8_t *s = smem + (size_t)stage * STAGE_BYTES;
                     mbar_expect_tx(&bar.full[stage], STAGE_BYTES);
-                    tma_load_2d(s, &map_ah, &bar.full[stage], kb * BK, arow);
-                    tma_load_2d(s + TILE_BYTES, &map_al, &bar.full[stage], kb * BK, arow);
-                    tma_load_2d(s + 2 * TILE_BYTES, &map_bh, &bar.full[stage], kb * BK, brow);
-                    tma_load_2d(s + 3 * TILE_BYTES, &map_bl, &bar.full[stage], kb * BK, brow);
+                    tma_load_2d(s, &map_ah, &bar.full[stage], (p.a_kb0 + kb) * BK, arow);
+                    tma_load_2d(s + TILE_BYTES, &map_al, &bar.full[stage], (p.a_kb0 + kb) * BK, arow);
+                    tma_load_2d(s + 2 * TILE_BYTES, &map_bh, &bar.full[stage], (p.b_kb0 + kb) * BK, brow);
+                    tma_load_2d(s + 3 * TILE_BYTES, &map_bl, &bar.full[stage], (p.b_kb0 + kb) * BK, brow);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -168,12 +170,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
             mbar_wait(&bar.tmem_full[buf], (it >> 1) & 1);
             tc_fence_after();
             const int m = tm * BM + q * 32 + lane;
+            const bool row_ok = m < p.m_valid;
             float *crow = p.C + (long)b * p.c_batch + (long)m * p.ldc + tn * BN;
             const bool empty = kb1 <= kb0;
 #pragma unroll 1
             for (int ch = 0; ch < BN / 32; ++ch) {
                 uint32_t v[32];
                 tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + ch * 32), v);
+                if (!row_ok) continue;
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
                     float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -249,6 +253,8 @@ int gemm_tf32x3_nt(const GemmArgs &g, void *ws, size_t ws_bytes, cudaStream_t st
         return GQ_ERR_CUDA;
     }
     KParams p;
+    p.a_row0 = p.b_row0 = p.a_kb0 = p.b_kb0 = 0;
+    p.m_valid = g.M;
     p.C = g.C; p.ldc = g.ldc; p.c_batch = g.c_batch; p.M = g.M; p.N = g.N; p.nkb = Kp / BK; p.batch = g.batch;
     const int ntm = g.M / BM;
     p.ntn = g.N / BN;
@@ -259,6 +265,40 @@ int gemm_tf32x3_nt(const GemmArgs &g, void *ws, size_t ws_bytes, cudaStream_t st
     GQ_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     const int ntiles = p.tiles_per_batch * g.batch;
     const int grid = ntiles < num_sms() ? ntiles : num_sms();
+    gemm_tf32x3_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mah, mal, mbh, mbl, p);
+    gq_count_launches(1);
+    GQ_CHECK_CUDA(cudaGetLastError());
+    return GQ_OK;
+}
+
+// Same GEMM on operands the caller has already split (hi/lo arrays with their own pitch); the operand blocks start at
+// (row0, k0) inside those arrays.  K and k0 must be multiples of 32, pitches multiples of 4 floats, arrays 16-byte aligned.
+int gemm_tf32x3_nt_presplit(const PreSplit &A, const PreSplit &B, float *C, long ldc, int M, int m_valid, int N, int K, float alpha,
+                            float beta, cudaStream_t st) {
+    if (M % BM || N % BN || K % BK || A.k0 % BK || B.k0 % BK || M <= 0 || N <= 0 || K <= 0) {
+        gq_set_error("gemm_tf32x3_nt_presplit: bad shape M=%d N=%d K=%d", M, N, K);
+        return GQ_ERR_INVALID;
+    }
+    CUtensorMap mah, mal, mbh, mbl;
+    const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    bool ok = make_map_2d(&mah, (void *)A.hi, dt, 4, (uint64_t)A.rows, (uint64_t)A.pitch, BK, BM) &&
+              make_map_2d(&mal, (void *)A.lo, dt, 4, (uint64_t)A.rows, (uint64_t)A.pitch, BK, BM) &&
+              make_map_2d(&mbh, (void *)B.hi, dt, 4, (uint64_t)B.rows, (uint64_t)B.pitch, BK, BN) &&
+              make_map_2d(&mbl, (void *)B.lo, dt, 4, (uint64_t)B.rows, (uint64_t)B.pitch, BK, BN);
+    if (!ok) {
+        gq_set_error("gemm_tf32x3_nt_presplit: cuTensorMapEncodeTiled failed");
+        return GQ_ERR_CUDA;
+    }
+    KParams p;
+    p.a_row0 = A.row0; p.b_row0 = B.row0; p.a_kb0 = A.k0 / BK; p.b_kb0 = B.k0 / BK;
+    p.m_valid = m_valid;
+    p.C = C; p.ldc = ldc; p.c_batch = 0; p.M = M; p.N = N; p.nkb = K / BK; p.batch = 1;
+    p.ntn = N / BN;
+    p.tiles_per_batch = (M / BM) * p.ntn;
+    p.alpha = alpha; p.beta = beta; p.tile_mode = TM_FULL; p.k_mode = KM_FULL;
+    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    GQ_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    const int grid = p.tiles_per_batch < num_sms() ? p.tiles_per_batch : num_sms();
     gemm_tf32x3_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mah, mal, mbh, mbl, p);
     gq_count_launches(1);
     GQ_CHECK_CUDA(cudaGetLastError());

@@ -24,7 +24,13 @@ struct GemmArgs {
     bool same_ab;                             // B is A (SYRK): the operand is split once
 };
 
+// An operand whose hi / lo parts already exist: (rows x pitch) fp32 arrays; the block used starts at (row0, k0).
+struct PreSplit { const float *hi; const float *lo; long pitch; long rows; int row0; int k0; };
+
 size_t workspace_bytes(int M, int N, int K, int batch, bool same_ab);
+// M: multiple of 128 (rows of the A arrays); only rows < m_valid of C are touched.
+int gemm_tf32x3_nt_presplit(const PreSplit &A, const PreSplit &B, float *C, long ldc, int M, int m_valid, int N, int K, float alpha,
+                            float beta, cudaStream_t st);
 int gemm_tf32x3_nt(const GemmArgs &g, void *ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace tg

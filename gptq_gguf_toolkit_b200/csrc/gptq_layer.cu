@@ -13,6 +13,7 @@
 //     over its 128 k's in ascending order, then ONE subtraction from w -- bit-identical to addmm_ on CPU.
 //   * The scale/min search, the 128 sequential column steps (rank-1 updates held in registers, 8 lanes
 //     per row), the GGUF bit-pack and the dequantised write-back are fused in shared memory.
+#include "gemm_tf32.cuh"
 #include "tile.cuh"
 
 namespace {
@@ -38,6 +39,10 @@ struct LayerParams {
     void *wdeq;
     int wdeq_dtype;
     uint32_t *flags;
+    // GQ_MODE_FAST: the kernel handles super-blocks [sb_begin, sb_end) of an already updated W (the rank-k updates
+    // between super-blocks run as tcgen05 GEMMs) and also emits the hi/lo TF32 split of its errors.
+    int sb_begin, sb_end, fast;
+    float *e_hi, *e_lo;     // (rows padded to 128) x 256, only in fast mode
 };
 
 struct __align__(16) Smem {
@@ -188,13 +193,24 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const int id = tid + NT * m, row = id >> 5, c4 = id & 31;
-            if (r0 + row < p.d_row)
-                *reinterpret_cast<float4 *>(p.W + (size_t)(r0 + row) * ld + c1 + 4 * c4) =
-                    *reinterpret_cast<const float4 *>(sm.Et + row * 128 + 4 * c4);
+            if (r0 + row < p.d_row) {
+                const float4 e = *reinterpret_cast<const float4 *>(sm.Et + row * 128 + 4 * c4);
+                *reinterpret_cast<float4 *>(p.W + (size_t)(r0 + row) * ld + c1 + 4 * c4) = e;
+                if (p.fast) {      // operands of the next tcgen05 rank-256 update: hi = TF32 part, lo = remainder
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(e.x) & 0xFFFFE000u); l.x = __fsub_rn(e.x, h.x);
+                    h.y = __uint_as_float(__float_as_uint(e.y) & 0xFFFFE000u); l.y = __fsub_rn(e.y, h.y);
+                    h.z = __uint_as_float(__float_as_uint(e.z) & 0xFFFFE000u); l.z = __fsub_rn(e.z, h.z);
+                    h.w = __uint_as_float(__float_as_uint(e.w) & 0xFFFFE000u); l.w = __fsub_rn(e.w, h.w);
+                    const size_t o = (size_t)(r0 + row) * 256 + (c1 & 255) + 4 * c4;
+                    *reinterpret_cast<float4 *>(p.e_hi + o) = h;
+                    *reinterpret_cast<float4 *>(p.e_lo + o) = l;
+                }
+            }
         }
     };
 
-    for (int sb = 0; sb < nsb; ++sb) {
+    for (int sb = p.sb_begin; sb < p.sb_end; ++sb) {
         const int c = sb * GQ_QK_K;
         float w[8][4];
 #pragma unroll
@@ -204,7 +220,7 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
             w[i][0] = v.x; w[i][1] = v.y; w[i][2] = v.z; w[i][3] = v.w;
         }
         __syncthreads();   // previous super-block is completely done with the shared buffers
-        rank_update<false>(w, p, sm, r0, c, 0, c, tid, rg, ch, lane);
+        rank_update<false>(w, p, sm, r0, c, 0, p.fast ? 0 : c, tid, rg, ch, lane);   // fast mode: already applied by GEMMs
 #pragma unroll
         for (int i = 0; i < 8; ++i)
             *reinterpret_cast<float4 *>(sm.Wt + wt_idx4(8 * rg + i, ch * 32 + lane)) =
@@ -282,10 +298,114 @@ template <int QT> int launch_layer(const LayerParams &p, cudaStream_t st) {
 
 void gq_fill_search_params(SearchParams &sp, int maxq, double rmin, double rdelta, int nstep);
 
+// ---- optional kernel-level profiling of the fast path (bench.py: rank-k GEMM time measured live with CUDA events) ----
+#include <vector>
+namespace {
+struct ProfEvent { cudaEvent_t a, b; int kind; };   // kind 0 = fused search/column-loop kernel, 1 = tcgen05 rank-k GEMM
+bool g_prof_on = false;
+std::vector<ProfEvent> g_prof;
+struct ProfScope {
+    cudaStream_t st; int kind; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(cudaStream_t s, int k) : st(s), kind(k) {
+        if (g_prof_on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+    }
+    ~ProfScope() {
+        if (a) { cudaEventRecord(b, st); g_prof.push_back({a, b, kind}); }
+    }
+};
+}  // namespace
+
+extern "C" GQ_API void gq_profile_enable(int on) { g_prof_on = on != 0; }
+// Synchronises, sums the recorded spans by kind (milliseconds, launch counts), clears the record.
+extern "C" GQ_API int gq_profile_read(float ms[2], int counts[2]) {
+    ms[0] = ms[1] = 0.f; counts[0] = counts[1] = 0;
+    for (auto &e : g_prof) {
+        if (cudaEventSynchronize(e.b) != cudaSuccess) return GQ_ERR_CUDA;
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e.a, e.b);
+        ms[e.kind] += t; counts[e.kind] += 1;
+        cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    }
+    g_prof.clear();
+    return GQ_OK;
+}
+
+namespace {
+
+// Ut = U^T split into TF32 hi / lo parts (fast mode's B operand must be K-contiguous: B[n][k] = U[k][n] = Ut[n][k])
+__global__ void __launch_bounds__(256) transpose_split_kernel(const float *__restrict__ U, int n, float *__restrict__ hi,
+                                                              float *__restrict__ lo) {
+    __shared__ float t[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) t[r][tx] = U[(size_t)(r0 + r) * n + c0 + tx];
+    __syncthreads();
+    for (int c = ty; c < 32; c += 8) {
+        const float x = t[tx][c];
+        const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+        hi[(size_t)(c0 + c) * n + r0 + tx] = h;
+        lo[(size_t)(c0 + c) * n + r0 + tx] = __fsub_rn(x, h);
+    }
+}
+
+size_t fast_ws_bytes(int d_row, int d_col) {
+    const size_t n = (size_t)d_col, mp = ((size_t)d_row + 127) / 128 * 128;
+    return 2 * n * n * sizeof(float) + 2 * mp * 256 * sizeof(float) + 4096;
+}
+
+template <int QT> int run_layer(LayerParams p, int mode, void *ws, size_t ws_bytes, cudaStream_t st) {
+    const int nsb = p.d_col / GQ_QK_K;
+    p.fast = 0; p.e_hi = p.e_lo = nullptr; p.sb_begin = 0; p.sb_end = nsb;
+    if (mode == GQ_MODE_EXACT) {
+        ProfScope ps(st, 0);
+        return launch_layer<QT>(p, st);
+    }
+    // ---- GQ_MODE_FAST: right-looking at super-block granularity.  Per 256-column super-block one launch of the fused
+    // search / column-loop kernel, then ONE tcgen05 3xTF32 GEMM  W[:, c+256:] -= E[:, c:c+256] * U[c:c+256, c+256:].
+    if (ws == nullptr || ws_bytes < fast_ws_bytes(p.d_row, p.d_col)) {
+        gq_set_error("gq_gptq_quantize: fast mode needs %zu workspace bytes", fast_ws_bytes(p.d_row, p.d_col));
+        return GQ_ERR_WORKSPACE;
+    }
+    const int n = p.d_col, mp = (p.d_row + 127) / 128 * 128;
+    float *ut_hi = reinterpret_cast<float *>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+    float *ut_lo = ut_hi + (size_t)n * n;
+    float *e_hi = ut_lo + (size_t)n * n;
+    float *e_lo = e_hi + (size_t)mp * 256;
+    GQ_CHECK_CUDA(cudaMemsetAsync(e_hi, 0, 2 * (size_t)mp * 256 * sizeof(float), st));   // padded rows stay zero
+    transpose_split_kernel<<<dim3(n / 32, n / 32), 256, 0, st>>>(p.U, n, ut_hi, ut_lo);
+    gq_count_launches(1);
+    p.fast = 1; p.e_hi = e_hi; p.e_lo = e_lo;
+    for (int sb = 0; sb < nsb; ++sb) {
+        p.sb_begin = sb; p.sb_end = sb + 1;
+        int rc;
+        {
+            ProfScope ps(st, 0);
+            rc = launch_layer<QT>(p, st);
+        }
+        if (rc) return rc;
+        const int c = sb * GQ_QK_K, ntrail = n - c - GQ_QK_K;
+        if (ntrail > 0) {
+            tg::PreSplit A{e_hi, e_lo, 256, mp, 0, 0};
+            tg::PreSplit B{ut_hi, ut_lo, n, n, c + GQ_QK_K, c};
+            {
+                ProfScope ps(st, 1);
+                rc = tg::gemm_tf32x3_nt_presplit(A, B, p.W + c + GQ_QK_K, p.d_col, mp, p.d_row, ntrail, GQ_QK_K, -1.0f, 1.0f, st);
+            }
+            if (rc) return rc;
+        }
+    }
+    return GQ_OK;
+}
+
+}  // namespace
+
+extern "C" size_t gq_gptq_workspace_bytes(int d_row, int d_col, int mode) {
+    return mode == GQ_MODE_FAST ? fast_ws_bytes(d_row, d_col) : 0;
+}
+
 extern "C" int gq_gptq_quantize(float *W, const float *U, int d_row, int d_col, int qtype, int block_size,
                                 double rmin, double rdelta, int nstep, int mode, void *qweight, uint16_t *d,
                                 void *sq, uint16_t *dmin, void *zq, uint8_t *packed, void *wdeq, int wdeq_dtype,
-                                uint32_t *search_flags, gq_stream_t stream) {
+                                uint32_t *search_flags, void *workspace, size_t ws_bytes, gq_stream_t stream) {
     FmtInfo f;
     GQ_REQUIRE(gq_fmt_info(qtype, f), "gq_gptq_quantize: unknown q_type %d", qtype);
     GQ_REQUIRE(W && U && qweight && d && sq && dmin && zq, "gq_gptq_quantize: null pointer");
@@ -298,10 +418,7 @@ extern "C" int gq_gptq_quantize(float *W, const float *U, int d_row, int d_col, 
         gq_set_error("gq_gptq_quantize: block_size=%d not implemented (only 128, the run_quant.sh default)", block_size);
         return GQ_ERR_UNSUPPORTED;
     }
-    if (mode != GQ_MODE_EXACT) {
-        gq_set_error("gq_gptq_quantize: mode=%d not implemented in this build (GQ_MODE_EXACT only)", mode);
-        return GQ_ERR_UNSUPPORTED;
-    }
+    GQ_REQUIRE(mode == GQ_MODE_EXACT || mode == GQ_MODE_FAST, "gq_gptq_quantize: unknown mode %d", mode);
     LayerParams p;
     p.W = W; p.U = U; p.d_row = d_row; p.d_col = d_col;
     gq_fill_search_params(p.sp, (1 << f.bits) - 1, rmin, rdelta, nstep);
@@ -309,10 +426,10 @@ extern "C" int gq_gptq_quantize(float *W, const float *U, int d_row, int d_col, 
     p.packed = packed; p.wdeq = wdeq; p.wdeq_dtype = wdeq_dtype; p.flags = search_flags;
     cudaStream_t st = (cudaStream_t)stream;
     switch (qtype) {
-    case GQ_Q2_K: return launch_layer<GQ_Q2_K>(p, st);
-    case GQ_Q3_K: return launch_layer<GQ_Q3_K>(p, st);
-    case GQ_Q4_K: return launch_layer<GQ_Q4_K>(p, st);
-    case GQ_Q5_K: return launch_layer<GQ_Q5_K>(p, st);
-    default: return launch_layer<GQ_Q6_K>(p, st);
+    case GQ_Q2_K: return run_layer<GQ_Q2_K>(p, mode, workspace, ws_bytes, st);
+    case GQ_Q3_K: return run_layer<GQ_Q3_K>(p, mode, workspace, ws_bytes, st);
+    case GQ_Q4_K: return run_layer<GQ_Q4_K>(p, mode, workspace, ws_bytes, st);
+    case GQ_Q5_K: return run_layer<GQ_Q5_K>(p, mode, workspace, ws_bytes, st);
+    default: return run_layer<GQ_Q6_K>(p, mode, workspace, ws_bytes, st);
     }
 }

@@ -40,6 +40,20 @@ def launch_count() -> int:
     return int(L.load().gq_launch_count())
 
 
+def profile_enable(on: bool) -> None:
+    """Record CUDA events around the column-loop kernel / rank-k GEMM launches (see gq_profile_enable)."""
+    L.load().gq_profile_enable(1 if on else 0)
+
+
+def profile_read() -> dict:
+    """{'panel_ms', 'panel_launches', 'rankk_gemm_ms', 'rankk_gemm_launches'} since the last read; synchronises."""
+    import ctypes as C
+    ms = (C.c_float * 2)()
+    n = (C.c_int * 2)()
+    L.check(L.load().gq_profile_read(ms, n))
+    return {"panel_ms": ms[0], "panel_launches": n[0], "rankk_gemm_ms": ms[1], "rankk_gemm_launches": n[1]}
+
+
 def _workspace(device, nbytes: int) -> torch.Tensor:
     """One growing scratch buffer per device (torch caching allocator owns the memory)."""
     key = (device.type, device.index)
@@ -119,11 +133,14 @@ def gptq_quantize(W: torch.Tensor, U: torch.Tensor, q_type: int, block_size: int
     d_row, d_col = W.shape
     qweight, d, sq, dmin, zq, pk, wd = alloc_outputs(q_type, d_row, d_col, W.device, packed, wdeq_dtype)
     flags = torch.zeros(d_col // QK_K, 2, dtype=torch.int32, device=W.device) if search_flags else None
+    lib = L.load()
+    nws = lib.gq_gptq_workspace_bytes(d_row, d_col, int(mode))
+    ws = _workspace(W.device, nws) if nws else None
     with _span("gptq"):
-        L.check(L.load().gq_gptq_quantize(
+        L.check(lib.gq_gptq_quantize(
             L.ptr(W), L.ptr(U), d_row, d_col, int(q_type), int(block_size), float(rmin), float(rdelta), int(nstep), int(mode),
             L.ptr(qweight), L.ptr(d), L.ptr(sq), L.ptr(dmin), L.ptr(zq), L.ptr(pk), L.ptr(wd),
-            L.dtype_code(wdeq_dtype) if wdeq_dtype is not None else 0, L.ptr(flags), L.stream_of(W.device)))
+            L.dtype_code(wdeq_dtype) if wdeq_dtype is not None else 0, L.ptr(flags), L.ptr(ws), nws, L.stream_of(W.device)))
     return qweight, d, sq, dmin, zq, pk, wd, flags
 
 

@@ -289,7 +289,8 @@ class Quantizer:
     def _sharded_gptq(self, W, U, qt, dtype, rank, world):
         kw = self.quantizer_kwargs
         args = dict(block_size=kw.get("block_size", 128) or W.shape[1], rmin=kw.get("rmin", -1.0),
-                    rdelta=kw.get("rdelta", 0.1), nstep=kw.get("nstep", 20), packed=True, wdeq_dtype=dtype)
+                    rdelta=kw.get("rdelta", 0.1), nstep=kw.get("nstep", 20), packed=True, wdeq_dtype=dtype,
+                    mode={"exact": 0, "fast": 1}[kw.get("mode", "exact")])
         if world == 1:
             return ops.gptq_quantize(W, U, qt, **args)[:7]
         total = W.shape[0]

@@ -107,12 +107,21 @@ GQ_API int gq_prepare(float *H, const float *W, int d_row, int d_col, float rel_
  *          candidate for the whole call when no group is valid (quant_utils.py:250-252); this library
  *          never skips, so (flags[2s+1] & ~flags[2s]) != 0 marks the (degenerate) inputs on which the
  *          two can differ.  Must be zero-initialised by the caller.
- * block_size must be 128 (the reference's run_quant.sh default). */
+ * block_size must be 128 (the reference's run_quant.sh default).
+ * mode GQ_MODE_FAST needs gq_gptq_workspace_bytes() of scratch (GQ_MODE_EXACT needs none): the rank-k updates between
+ * 256-column super-blocks then run as tcgen05 3xTF32 GEMMs (fp32-class accuracy, NOT bit-identical to the reference). */
+GQ_API size_t gq_gptq_workspace_bytes(int d_row, int d_col, int mode);
 GQ_API int gq_gptq_quantize(float *W, const float *U, int d_row, int d_col, int qtype, int block_size,
                      double rmin, double rdelta, int nstep, int mode,
                      void *qweight, uint16_t *d, void *sq, uint16_t *dmin, void *zq,
                      uint8_t *packed, void *wdeq, int wdeq_dtype, uint32_t *search_flags,
-                     gq_stream_t stream);
+                     void *workspace, size_t ws_bytes, gq_stream_t stream);
+
+/* Kernel-level timing of gq_gptq_quantize for benchmarks: when enabled, CUDA events are recorded around every launch of
+ * the fused search / column-loop kernel (kind 0) and of the tcgen05 rank-k GEMM of GQ_MODE_FAST (kind 1).
+ * gq_profile_read synchronises on the recorded events, returns summed milliseconds and launch counts per kind, and clears. */
+GQ_API void gq_profile_enable(int on);
+GQ_API int gq_profile_read(float ms[2], int counts[2]);
 
 /* RTN K-quant without a Hessian -- replaces Quantizer._quant_non_block_module
  * (quantizer.py:278-330).  W: (d_row, d_col) of w_dtype, read-only; arithmetic is fp32. */

@@ -56,6 +56,13 @@ def main():
             mn, av = timed(lambda: ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16), warm=1, it=2)
             fl = rows * n * (n - 128)
             print(f"gptq {rows}x{n}: {mn:.2f} ms -> rank-k {fl / mn / 1e9:.1f} TFLOP/s", flush=True)
+            mn, av = timed(lambda: ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16, mode=1), warm=1, it=2)
+            ops.profile_enable(True)
+            ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16, mode=1)
+            pr = ops.profile_read()
+            ops.profile_enable(False)
+            print(f"gptq FAST {rows}x{n}: {mn:.2f} ms -> rank-k {fl / mn / 1e9:.1f} TFLOP/s; panel {pr['panel_ms']:.2f} ms/{pr['panel_launches']}, "
+                  f"tcgen05 rank-k GEMMs {pr['rankk_gemm_ms']:.2f} ms/{pr['rankk_gemm_launches']} -> {rows * n * (n - 256) / max(pr['rankk_gemm_ms'], 1e-9) / 1e9:.0f} TFLOP/s", flush=True)
     if "rtn" in what:
         W = torch.randn(128256, 4096, device="cuda").to(torch.bfloat16)
         mn, av = timed(lambda: ops.rtn_quantize(W, 12, wdeq_dtype=torch.bfloat16), warm=1, it=2)
