@@ -43,6 +43,24 @@ struct LayerParams {
     // between super-blocks run as tcgen05 GEMMs) and also emits the hi/lo TF32 split of its errors.
     int sb_begin, sb_end, fast;
     float *e_hi, *e_lo;     // (rows padded to 128) x 256, only in fast mode
+    unsigned long long *clk;   // optional (gq_debug_phase_clocks): 8 per-phase cycle counters summed over CTAs
+};
+
+// phase ids of the optional cycle counters
+enum { PH_RANK = 0, PH_SEARCH, PH_FINAL, PH_SERIAL0, PH_MID, PH_SERIAL1, PH_EMIT, PH_COUNT };
+struct PhaseClock {
+    unsigned long long *out;
+    long long t;
+    __device__ __forceinline__ PhaseClock(unsigned long long *o) : out(o), t(0) {
+        if (out && threadIdx.x == 0) t = clock64();
+    }
+    __device__ __forceinline__ void lap(int ph) {
+        if (out && threadIdx.x == 0) {
+            const long long n = clock64();
+            atomicAdd(out + ph, (unsigned long long)(n - t));
+            t = n;
+        }
+    }
 };
 
 struct __align__(16) Smem {
@@ -210,6 +228,7 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
         }
     };
 
+    PhaseClock pc(p.clk);
     for (int sb = p.sb_begin; sb < p.sb_end; ++sb) {
         const int c = sb * GQ_QK_K;
         float w[8][4];
@@ -226,6 +245,7 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
             *reinterpret_cast<float4 *>(sm.Wt + wt_idx4(8 * rg + i, ch * 32 + lane)) =
                 make_float4(w[i][0], w[i][1], w[i][2], w[i][3]);
         __syncthreads();
+        pc.lap(PH_RANK);
 
         // scale / min search on the live tile (gptq.py:240-245 -> quant_utils.py:90-145); U's diagonal
         // block for the first 128 columns streams in underneath it.
@@ -234,6 +254,7 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
         tile_search<QT, R, NT>(sm.Wt, sm.gsc, sm.gzr, p.sp, vmask, amask);
         publish_flags(p.flags ? p.flags + 2 * sb : nullptr, vmask, amask);
         __syncthreads();
+        pc.lap(PH_SEARCH);
         if (tid < R) {
             tile_finalize_row<QT, R>(tid, sm.gsc, sm.gzr, sm.rs);
             if (r0 + tid < p.d_row) {
@@ -249,9 +270,11 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
         }
         cp_async_wait<0>();
         __syncthreads();
+        pc.lap(PH_FINAL);
 
         serial_block<QT>(sm, 0, srow, q8);
         __syncthreads();
+        pc.lap(PH_SERIAL0);
         store_E(c);
         __syncthreads();   // E of block 0 visible to the whole CTA; Ud is free again
 
@@ -273,14 +296,17 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
         load_Ud(c + 128);
         cp_async_wait<0>();
         __syncthreads();
+        pc.lap(PH_MID);
 
         serial_block<QT>(sm, 1, srow, q8);
         __syncthreads();
+        pc.lap(PH_SERIAL1);
         store_E(c + 128);
 
         // outputs of the finished super-block: codes, GGUF bytes, dequantised weights
         tile_emit<QT, R, NT>(sm.Wt, sm.codes, sm.rs, r0, p.d_row, ld, c, sb, nsb, p.qweight, p.packed, p.wdeq,
                              p.wdeq_dtype);
+        pc.lap(PH_EMIT);
     }
 }
 
@@ -315,6 +341,10 @@ struct ProfScope {
 };
 }  // namespace
 
+unsigned long long *g_phase_clk = nullptr;
+// debug hook (not part of the reference-facing API): device array of 8 u64 that the column-loop kernel adds its
+// per-phase cycle counts to (thread 0 of every CTA); nullptr switches the counters off.
+extern "C" GQ_API void gq_debug_phase_clocks(unsigned long long *dev8) { g_phase_clk = dev8; }
 extern "C" GQ_API void gq_profile_enable(int on) { g_prof_on = on != 0; }
 // Synchronises, sums the recorded spans by kind (milliseconds, launch counts), clears the record.
 extern "C" GQ_API int gq_profile_read(float ms[2], int counts[2]) {
@@ -424,6 +454,7 @@ extern "C" int gq_gptq_quantize(float *W, const float *U, int d_row, int d_col, 
     gq_fill_search_params(p.sp, (1 << f.bits) - 1, rmin, rdelta, nstep);
     p.qweight = (uint8_t *)qweight; p.d = d; p.sq = (uint8_t *)sq; p.dmin = dmin; p.zq = (uint8_t *)zq;
     p.packed = packed; p.wdeq = wdeq; p.wdeq_dtype = wdeq_dtype; p.flags = search_flags;
+    p.clk = g_phase_clk;
     cudaStream_t st = (cudaStream_t)stream;
     switch (qtype) {
     case GQ_Q2_K: return run_layer<GQ_Q2_K>(p, mode, workspace, ws_bytes, st);

@@ -7,6 +7,7 @@ five K-quant tensors are always returned in the reference's order
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Optional, Tuple
 
 import torch
@@ -54,11 +55,16 @@ def profile_read() -> dict:
     return {"panel_ms": ms[0], "panel_launches": n[0], "rankk_gemm_ms": ms[1], "rankk_gemm_launches": n[1]}
 
 
-def _workspace(device, nbytes: int) -> torch.Tensor:
-    """One growing scratch buffer per device (torch caching allocator owns the memory)."""
-    key = (device.type, device.index)
+def _workspace(device, nbytes: int, slot: int = 0) -> torch.Tensor:
+    """One growing scratch buffer per (device, slot); callers that run ops concurrently on several streams
+    give every stream its own slot (torch caching allocator owns the memory)."""
+    key = (device.type, device.index, slot)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            # the old buffer may still be in use by work enqueued on a side stream: keep it alive until the
+            # device is idle instead of handing it back to the allocator of the current stream
+            torch.cuda.synchronize(device)
         _ws_cache[key] = ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
     return ws
 
@@ -106,9 +112,12 @@ def pre_step(H: torch.Tensor, W: torch.Tensor) -> None:
     L.check(L.load().gq_pre_step(L.ptr(H), L.ptr(W), W.shape[0], W.shape[1], L.stream_of(H.device)))
 
 
-def prepare(H: torch.Tensor, W: torch.Tensor, rel_damp: float) -> Tuple[torch.Tensor, torch.Tensor]:
+def prepare(H: torch.Tensor, W: torch.Tensor, rel_damp: float, stream: Optional["torch.cuda.Stream"] = None,
+            slot: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
     """U = chol(inv(H + damp I), upper), row-major (gptq.py:305-324).  H is masked + damped in place.
-    Returns (U, not_pd) where not_pd is a device int32 scalar (1 => U is the identity)."""
+    Returns (U, not_pd) where not_pd is a device int32 scalar (1 => U is the identity).
+    stream: enqueue on this side stream instead of the current one (outputs are allocated on the CURRENT stream,
+    the side stream first waits for it; the caller waits on the side stream before consuming U).  slot: workspace slot."""
     L.require_cuda(H, W)
     assert H.dtype == torch.float32 and H.is_contiguous() and W.dtype == torch.float32 and W.is_contiguous()
     d_row, d_col = W.shape
@@ -116,10 +125,13 @@ def prepare(H: torch.Tensor, W: torch.Tensor, rel_damp: float) -> Tuple[torch.Te
     U = torch.empty(d_col, d_col, dtype=torch.float32, device=H.device)
     flag = torch.zeros(1, dtype=torch.int32, device=H.device)
     nws = lib.gq_prepare_workspace_bytes(d_col)
-    ws = _workspace(H.device, nws)
-    with _span("prepare"):
-        L.check(lib.gq_prepare(L.ptr(H), L.ptr(W), d_row, d_col, float(rel_damp), L.ptr(U), L.ptr(ws), nws,
-                               L.ptr(flag), L.stream_of(H.device)))
+    ws = _workspace(H.device, nws, slot)
+    if stream is not None:
+        stream.wait_stream(torch.cuda.current_stream(H.device))
+    with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
+        with _span("prepare"):
+            L.check(lib.gq_prepare(L.ptr(H), L.ptr(W), d_row, d_col, float(rel_damp), L.ptr(U), L.ptr(ws), nws,
+                                   L.ptr(flag), L.stream_of(H.device)))
     return U, flag
 
 

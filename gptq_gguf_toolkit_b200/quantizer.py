@@ -117,7 +117,8 @@ class Quantizer:
                  cpu_offload_activations: bool = False, verbose: bool = False,
                  # ---- additions over the reference ----
                  calibration_batch_size: int = 8, share_hessians: bool = True, keep_results: bool = False,
-                 save_packed: bool = True, timer: Optional[PhaseTimer] = None) -> None:
+                 save_packed: bool = True, timer: Optional[PhaseTimer] = None, early_exit_pass1: bool = True,
+                 overlap_prepare: bool = True) -> None:
         self.model = model
         self.data_loader = data_loader
         self.quantizable_modules = quantizable_modules
@@ -135,6 +136,10 @@ class Quantizer:
         self.share_hessians = share_hessians
         self.keep_results = keep_results
         self.save_packed = save_packed
+        self.early_exit_pass1 = early_exit_pass1
+        self.overlap_prepare = overlap_prepare
+        self._side_streams: list = []
+        self._mask_flags: list = []
         self.timer = timer or PhaseTimer(False)
         self.results: Dict[str, Dict[str, Any]] = {}    # module name -> data.pth dict (+ "packed"), if keep_results
         self.non_invertible: List[str] = []
@@ -199,40 +204,56 @@ class Quantizer:
 
     # -------------------------------------------------------------------------------------------
     def _prepare_hooks_and_handles(self, layers: Dict[str, nn.Module]):
-        """quantizer.py:222-237, plus Hessian sharing: layers that receive the very same input tensor object
-        during a forward are attached to one accumulator, which is updated once per forward."""
+        """quantizer.py:222-237, plus (a) Hessian sharing: layers that receive the very same input tensor object
+        during a forward are attached to one accumulator, which is updated once per forward; (b) pass-1 early
+        exit: the hooks are forward PRE-hooks (they see the same `inp[0]` as the reference's forward hooks), the
+        first forward of a block records the order in which the hooked layers fire, and every later forward is
+        interrupted (ForwardInterrupt) right after the last layer's Hessian update -- the reference discards the
+        output of pass 1 (quantizer.py:150-151), so the last projection's GEMM and the block tail are dead work."""
         handles: Dict[str, GPTQ] = {}
         hooks = {}
         seen: list = []      # [(input tensor, accumulator)] of the forward in flight (refs keep addresses unique)
-        grouping_done = {"v": False}
+        state = {"grouped": False, "order": [], "last": None, "fired": 0}
 
         def make_hook(name):
-            def _hook(_, inp, out):
+            def _hook(_, inp):
                 x = inp[0]
                 h = handles[name]
+                state["fired"] += 1
+                if not state["grouped"]:
+                    state["order"].append(name)
                 if not self.share_hessians:
                     h.update(x)
-                    return
-                for t, acc in seen:
-                    if t is x:
-                        if h.hessian is not acc:
-                            if grouping_done["v"]:
-                                raise RuntimeError(f"inconsistent input sharing for {name}")
-                            h.hessian.users -= 1
-                            h.hessian = acc
-                            acc.users += 1
-                        return
-                h.update(x)
-                seen.append((x, h.hessian))
+                else:
+                    for t, acc in seen:
+                        if t is x:
+                            if h.hessian is not acc:
+                                if state["grouped"]:
+                                    raise RuntimeError(f"inconsistent input sharing for {name}")
+                                h.hessian.users -= 1
+                                h.hessian = acc
+                                acc.users += 1
+                            break
+                    else:
+                        h.update(x)
+                        seen.append((x, h.hessian))
+                if state["last"] == name and state["fired"] == len(handles):
+                    raise ForwardInterrupt
             return _hook
 
         for layer_name, layer in layers.items():
             handles[layer_name] = self._create_handle(layer)
-            hooks[layer_name] = layer.register_forward_hook(make_hook(layer_name))
+            hooks[layer_name] = layer.register_forward_pre_hook(make_hook(layer_name))
 
         def end_of_forward():
             seen.clear()
-            grouping_done["v"] = True
+            if not state["grouped"]:
+                state["grouped"] = True
+                order = state["order"]
+                # early exit only when every hooked layer fired exactly once in the recorded forward
+                if self.early_exit_pass1 and len(order) == len(handles) == len(set(order)) and order:
+                    state["last"] = order[-1]
+            state["fired"] = 0
 
         return handles, hooks, end_of_forward
 
@@ -245,23 +266,40 @@ class Quantizer:
             groups.setdefault(id(h.hessian), []).append(name)
         kw = self.quantizer_kwargs
         rank, world = _rank(), _world()
-        for names in groups.values():
+        on_gpu = next(iter(handles.values())).layer.weight.is_cuda
+        overlap = self.overlap_prepare and on_gpu and len(groups) > 1
+        main = torch.cuda.current_stream() if on_gpu else None
+        # ---- phase A: per distinct Hessian: all-reduce, fp32 working copy, dead-channel fix, U = chol(inv(H)).
+        # With `overlap_prepare` every group's Cholesky chain runs on its own side stream (own workspace slot), so
+        # the latency-bound chains of the 4 groups of a block run concurrently and hide behind the column-loop
+        # kernels of the groups before them; the main stream only waits for the U it is about to consume.
+        plans = []
+        for gi, names in enumerate(groups.values()):
             hs = [handles[n] for n in names]
             acc = hs[0].hessian
             with self.timer.span("allreduce"):
                 acc.all_reduce()                                               # gptq.py:131-132
-            q_types = [quant_config.get(n.split(".")[-1], GGMLQuantizationType.Q4_K) for n in names]  # quantizer.py:249
-            dtype = hs[0].layer.weight.dtype
-            # fp32 working copy of all members, stacked row-wise (gptq.py:138)
             rows = [h.d_row for h in hs]
             with self.timer.span("prepare_host"):
+                # fp32 working copy of all members, stacked row-wise (gptq.py:138)
                 W = torch.cat([h.layer.weight.data.float() for h in hs], dim=0).contiguous()
                 ops.pre_step(acc.H, W)                                         # gptq.py:134-141
-                masks = torch.stack([(w == 0).all(dim=0) for w in W.split(rows, dim=0)])
-                if len(hs) > 1 and not bool((masks == masks[0:1]).all()):
-                    raise RuntimeError("layers sharing an input have different all-zero weight columns; "
-                                       "rerun with share_hessians=False")
-                U, not_pd = ops.prepare(acc.H, W, kw.get("rel_damp", 1e-2))    # gptq.py:305-324
+                if len(hs) > 1:
+                    masks = torch.stack([(w == 0).all(dim=0) for w in W.split(rows, dim=0)])
+                    self._mask_flags.append((names, (masks != masks[0:1]).any()))   # checked at the end (no host sync here)
+                side = self._side_stream(gi) if overlap else None
+                U, not_pd = ops.prepare(acc.H, W, kw.get("rel_damp", 1e-2), stream=side, slot=1 + gi if overlap else 0)  # gptq.py:305-324
+                done = None
+                if side is not None:
+                    done = torch.cuda.Event()
+                    done.record(side)
+            plans.append((names, hs, rows, W, U, not_pd, done))
+        # ---- phase B: the column loops, in module order, on the main stream
+        for names, hs, rows, W, U, not_pd, done in plans:
+            if done is not None:
+                main.wait_event(done)
+            q_types = [quant_config.get(n.split(".")[-1], GGMLQuantizationType.Q4_K) for n in names]  # quantizer.py:249
+            dtype = hs[0].layer.weight.dtype
             # sub-groups of equal q_type, keeping module order
             by_type: Dict[int, List[int]] = {}
             for i, qt in enumerate(q_types):
@@ -285,6 +323,14 @@ class Quantizer:
             self._not_pd_flags.append((names, not_pd))
             for h in hs:
                 h.reset()                                                      # quantizer.py:265
+        del plans
+
+    def _side_stream(self, i: int):
+        """Side streams for the Cholesky chains; earlier groups get the higher priority (their U is needed first)."""
+        while len(self._side_streams) <= i:
+            k = len(self._side_streams)
+            self._side_streams.append(torch.cuda.Stream(priority=-1 if k == 0 else 0))
+        return self._side_streams[i]
 
     def _sharded_gptq(self, W, U, qt, dtype, rank, world):
         kw = self.quantizer_kwargs
@@ -345,6 +391,7 @@ class Quantizer:
     def quantize(self, quant_config: Dict[str, GGMLQuantizationType]) -> None:
         device = self.device or next(self.model.parameters()).device
         self._not_pd_flags = []
+        self._mask_flags = []
         ops.set_timer(self.timer if self.timer.enabled else None)
         if self.save_dir is not None and _rank() == 0:
             os.makedirs(self.save_dir, exist_ok=True)
@@ -396,7 +443,10 @@ class Quantizer:
 
             with self.timer.span("forward1"):
                 for inp_args, inp_kwargs in batches:
-                    block(*to(inp_args, device=device), **to(inp_kwargs, device=device))
+                    try:
+                        block(*to(inp_args, device=device), **to(inp_kwargs, device=device))
+                    except ForwardInterrupt:      # raised by the last hooked layer's pre-hook (pass-1 early exit)
+                        pass
                     end_of_forward()
             for h in hooks.values():
                 h.remove()
@@ -435,6 +485,10 @@ class Quantizer:
             with self.timer.span("save_wait"):
                 self._saver.close()
             self._saver = None
+        for names, flag in self._mask_flags:      # deferred check (a device flag per shared-input group)
+            if bool(flag.item()):
+                raise RuntimeError(f"layers {names} share an input but have different all-zero weight columns; "
+                                   "rerun with share_hessians=False")
         if _dist_on():
             dist.barrier()
         ops.set_timer(None)

@@ -27,6 +27,26 @@ def timed(fn, warm=1, it=3):
     return min(ts), sum(ts) / len(ts)
 
 
+PHASES = ["rank_update", "search", "finalize", "serial0", "mid_update", "serial1", "emit"]
+
+
+def phase_clocks(fn, n_cta):
+    """Per-phase cycle counters of gptq_layer_kernel (gq_debug_phase_clocks), averaged per CTA."""
+    import ctypes as C
+    from gptq_gguf_toolkit_b200 import _lib
+    lib = _lib.load()
+    lib.gq_debug_phase_clocks.argtypes = [C.c_void_p]
+    lib.gq_debug_phase_clocks.restype = None
+    buf = torch.zeros(8, dtype=torch.int64, device="cuda")
+    lib.gq_debug_phase_clocks(C.c_void_p(buf.data_ptr()))
+    fn()
+    torch.cuda.synchronize()
+    lib.gq_debug_phase_clocks(None)
+    c = buf.cpu().tolist()
+    tot = sum(c[:7]) or 1
+    print("   phase cycles per CTA: " + ", ".join(f"{n} {v / n_cta / 1e3:.0f}k ({100 * v / tot:.0f}%)" for n, v in zip(PHASES, c)), flush=True)
+
+
 def spd(n, dev="cuda"):
     x = torch.randn(2 * n, n, device=dev)
     H = (x.T @ x) / n
@@ -56,6 +76,7 @@ def main():
             mn, av = timed(lambda: ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16), warm=1, it=2)
             fl = rows * n * (n - 128)
             print(f"gptq {rows}x{n}: {mn:.2f} ms -> rank-k {fl / mn / 1e9:.1f} TFLOP/s", flush=True)
+            phase_clocks(lambda: ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16), (rows + 31) // 32)
             mn, av = timed(lambda: ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16, mode=1), warm=1, it=2)
             ops.profile_enable(True)
             ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16, mode=1)

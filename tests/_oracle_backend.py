@@ -40,7 +40,7 @@ def pre_step(H, W):
     H[idx, idx] = 1
 
 
-def prepare(H, W, rel_damp):
+def prepare(H, W, rel_damp, stream=None, slot=0):
     U, Hd, _, bad = orc.prepare(_np(H), _np(W), float(rel_damp))
     H.copy_(torch.from_numpy(Hd))
     return torch.from_numpy(U), torch.tensor([int(bad)], dtype=torch.int32)
