@@ -233,6 +233,10 @@ def main():
     ap.add_argument("--mode", type=str, default="both", choices=["exact", "fast", "both"],
                     help="exact: bit-identical fp32 rank-k (headline); fast: tcgen05 3xTF32 rank-k; both: headline exact + one fast step")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="ablation: Cholesky chains on the main stream")
+    ap.add_argument("--overlap", type=str, default="eager", choices=["eager", "staged"],
+                    help="side-stream Cholesky chains: overlap the column loops too (eager) or run before them (staged)")
+    ap.add_argument("--no-early-exit", action="store_true", help="ablation: run the full block in forward pass 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -283,7 +287,8 @@ def main():
                                             mode=mode or main_mode),
                       pre_block_modules=["model.embed_tokens"], block_modules="model.layers", post_block_modules=["lm_head"],
                       quant_non_block_modules=True, device=device, save_dir=None, keep_results=e2e,
-                      calibration_batch_size=args.batch, timer=timer)
+                      calibration_batch_size=args.batch, timer=timer, overlap_prepare=False if args.no_overlap else args.overlap,
+                      early_exit_pass1=not args.no_early_exit)
         if not e2e:
             restore_from_hbm()
         torch.cuda.synchronize()
@@ -343,6 +348,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         host_w = {n: t.to("cpu").pin_memory() for n, t in pristine.items()}
+        one_step(True)      # warm-up: fills torch's pinned-host cache with the result buffers (cudaHostAlloc is slow)
         secs, _, _, h2d, d2h, _ = one_step(True)
         e2e = {"value": secs, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": 1}
 

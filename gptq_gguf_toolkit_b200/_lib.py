@@ -8,7 +8,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libgq.so")
+SO_PATH = os.environ.get("GQ_LIB_PATH") or os.path.join(_HERE, "libgq.so")   # GQ_LIB_PATH: development variants
 
 GQ_OK, GQ_ERR_INVALID, GQ_ERR_CUDA, GQ_ERR_UNSUPPORTED, GQ_ERR_WORKSPACE = 0, 1, 2, 3, 4
 GQ_F32, GQ_F16, GQ_BF16 = 0, 1, 2

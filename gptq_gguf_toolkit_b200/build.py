@@ -37,18 +37,20 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), so: str = SO, bdir_name: str = "build") -> str:
+    """extra_flags / so / bdir_name: development variants (e.g. -DGQ_SERIAL_VARIANT=1 into libgq_v1.so), selected at
+    run time with GQ_LIB_PATH (see _lib.py); the product build uses the defaults."""
+    if so == SO and not force and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
-    bdir = os.path.join(HERE, "build")
+    bdir = os.path.join(HERE, bdir_name)
     os.makedirs(bdir, exist_ok=True)
     procs = []
     for src in sources():
         obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", src, "-o", obj]
+        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags) + ["-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
@@ -63,10 +65,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(f"nvcc failed on {src}", file=sys.stderr)
     if failed:
         raise RuntimeError("libgq build failed")
-    cmd = [nvcc, "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", so] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
-    return SO
+    return so
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    if defs:     # python -m gptq_gguf_toolkit_b200.build -DGQ_SERIAL_VARIANT=1 --tag v1  ->  libgq_v1.so
+        tag = sys.argv[sys.argv.index("--tag") + 1]
+        print(build(force=True, verbose="--verbose" in sys.argv, extra_flags=defs,
+                    so=os.path.join(HERE, f"libgq_{tag}.so"), bdir_name=f"build_{tag}"))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -10,7 +10,8 @@
 // the zero tiles of triangular operands are skipped through k-ranges per tile.
 //
 // Structure = hessian_tc.cu: persistent CTA per SM, warp-specialised (TMA producer / one-thread MMA issuer /
-// four epilogue warps), 3-stage mbarrier ring of 64 KB stages (A_hi, A_lo, B_hi, B_lo tiles of 128 x 32 fp32,
+// eight epilogue warps with a shared-memory transpose so that C moves in full 128-byte lines and is prefetched
+// underneath the MMAs), 3-stage mbarrier ring of 64 KB stages (A_hi, A_lo, B_hi, B_lo tiles of 128 x 32 fp32,
 // 128B-swizzled), M128 x N128 x K8 kind::tf32 MMAs, two 128-column TMEM accumulators.
 #include "gemm_tf32.cuh"
 #include "tc_common.cuh"
@@ -21,7 +22,9 @@ using namespace tc;
 constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3, UMMA_K = 8;
 constexpr int TILE_BYTES = BM * BK * 4;            // 16 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // A_hi, A_lo, B_hi, B_lo
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 384;                      // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;       // one 32 x 32 fp32 transpose tile per epilogue warp
 constexpr uint32_t TMEM_COLS = 256;
 
 struct Barriers {
@@ -31,7 +34,9 @@ struct Barriers {
     uint64_t tmem_empty[2];
     uint32_t tmem_base;
 };
-constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + sizeof(Barriers);
+constexpr size_t BAR_BYTES = 128;
+static_assert(sizeof(Barriers) <= BAR_BYTES, "barrier block");
+constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + BAR_BYTES + (size_t)EPI_WARPS * EPI_STAGE_BYTES;
 
 struct KParams {
     float *C;
@@ -100,7 +105,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&bar.full[s], 1); mbar_init(&bar.empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&bar.tmem_full[b], 1); mbar_init(&bar.tmem_empty[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&bar.tmem_full[b], 1); mbar_init(&bar.tmem_empty[b], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -161,35 +166,58 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
             }
         }
     } else if (warp >= 4) {   // ===== epilogue =====
-        const int q = warp & 3;
+        // Warp w may read TMEM lanes 32*(w%4)..+31 (= 32 rows of the tile); the eight warps split the tile's four
+        // 32-column chunks two each.  tcgen05.ld hands every lane one ROW of a chunk; a swizzled 32 x 32 staging
+        // tile in shared memory turns that into row-contiguous float4 so that C is read and written in full
+        // 128-byte lines (4 rows per warp instruction).  The C values are requested BEFORE waiting for the
+        // accumulator, i.e. they stream in underneath the tile's MMAs.
+        const int ew = warp - 4, q = warp & 3, half = ew >> 2;
+        float *stage = reinterpret_cast<float *>(smem + (size_t)STAGES * STAGE_BYTES + BAR_BYTES) + ew * (EPI_STAGE_BYTES / 4);
+        const int rr = lane >> 3, jj = lane & 7;
         int it = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             int b, tm, tn, kb0, kb1;
             decode_tile(p, t, b, tm, tn, kb0, kb1);
             const int buf = it & 1;
+            const int m0 = tm * BM + q * 32;
+            float *cbase = p.C + (long)b * p.c_batch + (long)m0 * p.ldc + tn * BN + half * 64 + 4 * jj;
+            float4 cpre[2][8];
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                for (int i8 = 0; i8 < 8; ++i8) {
+                    const int r = 4 * i8 + rr;
+                    cpre[cc][i8] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.beta != 0.0f && m0 + r < p.m_valid)
+                        cpre[cc][i8] = *reinterpret_cast<const float4 *>(cbase + (long)r * p.ldc + cc * 32);
+                }
             mbar_wait(&bar.tmem_full[buf], (it >> 1) & 1);
             tc_fence_after();
-            const int m = tm * BM + q * 32 + lane;
-            const bool row_ok = m < p.m_valid;
-            float *crow = p.C + (long)b * p.c_batch + (long)m * p.ldc + tn * BN;
             const bool empty = kb1 <= kb0;
-#pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
-                uint32_t v[32];
-                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + ch * 32), v);
-                if (!row_ok) continue;
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-                    float *cp = crow + ch * 32 + 4 * c4;
-                    if (p.beta != 0.0f) h = *reinterpret_cast<const float4 *>(cp);
+            for (int cc = 0; cc < 2; ++cc) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * 64 + cc * 32), v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4 *>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                    __uint_as_float(v[4 * j + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int i8 = 0; i8 < 8; ++i8) {
+                    const int r = 4 * i8 + rr;
+                    float4 a = *reinterpret_cast<const float4 *>(stage + r * 32 + ((jj ^ (r & 7)) << 2));
+                    if (empty) a = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 h = cpre[cc][i8];
                     float4 o;
-                    o.x = __fmaf_rn(p.alpha, empty ? 0.f : __uint_as_float(v[4 * c4 + 0]), __fmul_rn(p.beta, h.x));
-                    o.y = __fmaf_rn(p.alpha, empty ? 0.f : __uint_as_float(v[4 * c4 + 1]), __fmul_rn(p.beta, h.y));
-                    o.z = __fmaf_rn(p.alpha, empty ? 0.f : __uint_as_float(v[4 * c4 + 2]), __fmul_rn(p.beta, h.z));
-                    o.w = __fmaf_rn(p.alpha, empty ? 0.f : __uint_as_float(v[4 * c4 + 3]), __fmul_rn(p.beta, h.w));
-                    *reinterpret_cast<float4 *>(cp) = o;
+                    o.x = __fmaf_rn(p.alpha, a.x, __fmul_rn(p.beta, h.x));
+                    o.y = __fmaf_rn(p.alpha, a.y, __fmul_rn(p.beta, h.y));
+                    o.z = __fmaf_rn(p.alpha, a.z, __fmul_rn(p.beta, h.z));
+                    o.w = __fmaf_rn(p.alpha, a.w, __fmul_rn(p.beta, h.w));
+                    if (m0 + r < p.m_valid) *reinterpret_cast<float4 *>(cbase + (long)r * p.ldc + cc * 32) = o;
                 }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();

@@ -13,6 +13,7 @@
 //     over its 128 k's in ascending order, then ONE subtraction from w -- bit-identical to addmm_ on CPU.
 //   * The scale/min search, the 128 sequential column steps (rank-1 updates held in registers, 8 lanes
 //     per row), the GGUF bit-pack and the dequantised write-back are fused in shared memory.
+#include "f32x2.cuh"
 #include "gemm_tf32.cuh"
 #include "tile.cuh"
 
@@ -43,6 +44,7 @@ struct LayerParams {
     // between super-blocks run as tcgen05 GEMMs) and also emits the hi/lo TF32 split of its errors.
     int sb_begin, sb_end, fast;
     float *e_hi, *e_lo;     // (rows padded to 128) x 256, only in fast mode
+    f2_t nz2;                  // {-0.0f, -0.0f}, deliberately a run-time value (see f2_mul_nofuse)
     unsigned long long *clk;   // optional (gq_debug_phase_clocks): 8 per-phase cycle counters summed over CTAs
 };
 
@@ -70,12 +72,31 @@ struct __align__(16) Smem {
         float Ud[128 * 128];                 // diagonal block of U during the serial phase
     } u;
     float Et[R * 128];                       // errors of the current 128-column block
+    float Wq[R * 128];                       // dequantised values of the current block (copied into Wt when it is done)
     uint8_t codes[R * 256];
     float gsc[R * 16];
     float gzr[R * 16];
+    float dg_b[128];                         // diagonal of the current U block and its checked reciprocal (DivBy)
+    float dg_y[128];
+    float dummy_f[64];                       // sink of the non-owner lanes' stores in the serial phase
+    uint8_t dummy_b[32];
     RowScales<R> rs;
 };
 
+// Shared-memory layout of the (128 x 128) diagonal block of U for the serial phase: in row i the 16 values a
+// lane (l8 = j & 7) needs -- columns j = 8s + l8 -- are contiguous (64 B), 16-byte chunks XOR-swizzled by (l8 >> 1) & 3
+// so that the eight lanes of a row group read eight different bank groups with one LDS.128 each.
+__device__ __forceinline__ int ud_idx(int i, int j) {
+    const int l8 = j & 7, sgrp = j >> 3;
+    return i * 128 + l8 * 16 + ((((sgrp >> 2) ^ (l8 >> 1)) & 3) << 2) + (sgrp & 3);
+}
+
+// Variants of this loop that were built and measured on B200 and did NOT beat it (profiles/r01_gptq_kernel_notes.md,
+// profiles/microbench/): packed FFMA2 (same FMA rate, 5-6 register reads per issue), a column-per-warp mapping with a
+// k-major E (fewer shared-memory wavefronts, but 4-byte cp.async transposes cost more than they save), a
+// producer/consumer warp split with 8 x 8 register tiles (one warp per SM sub-partition issues an FFMA only every
+// ~1.65 cycles), and a TMA + mbarrier ring.  In isolation the FFMA pattern itself reaches 70 cycles per k (0.91 FFMA
+// per cycle per sub-partition); the pipelined loop runs at ~111.
 // tile(8 rows x 4 cols per thread) -= E[:, kbeg:kend] * U[kbeg:kend, window]; the reference's addmm_ arithmetic.
 // HALF: only the window's columns 128..255 are updated (warps with ch == 1 compute, all warps load).
 template <bool HALF>
@@ -150,40 +171,88 @@ __device__ __forceinline__ void rank_update(float (&w)[8][4], const LayerParams 
     __syncthreads();
 }
 
-// The 128 sequential column steps of one block (gptq.py:229-268).  8 lanes per row; lane q8 holds the
-// block's columns {8s + q8}.  Column i = 8s+q is broadcast from its owner, every lane of the row redoes the
-// (cheap) quantise/err arithmetic, then updates its not-yet-consumed columns:  w -= fl(err * U[i, j])  (no FMA).
-template <int QT>
-__device__ __forceinline__ void serial_block(Smem &sm, int blk, int srow, int q8) {
+// The 128 sequential column steps of one block (gptq.py:229-268), all 8 warps (two per SM sub-partition, so that
+// one warp's off-chain work fills the other's dependency stalls).  8 lanes per row; lane l8 holds the block's columns
+// {8s + l8}, s = 0..15, as 8 packed pairs.  Column i = 8s+q is broadcast from its owner, every lane of the row redoes
+// the (cheap) quantise/err arithmetic, then updates its not-yet-consumed columns:  w -= fl(err * U[i, j])
+// (two roundings: f2_mul_nofuse then sub.rn.f32x2).
+// The two divisions of the dependent chain -- (x + z) / max(s, eps) and (x - w_q) / U[i,i] -- use reciprocals prepared
+// off the chain (DivBy, f32x2.cuh).  SAFE = false: branch-free (DivBy::div_fast, stores through a select-ed pointer);
+// returns true if some quotient was outside the range in which div_fast is proven exact -- the caller then reruns the
+// block with SAFE = true (IEEE fallback inside DivBy::div).  The block's initial values are read from Wt, its
+// dequantised values go to `Wq` (a separate buffer), so a rerun starts from unchanged inputs.
+template <int QT, bool SAFE>
+__device__ __noinline__ bool serial_block_impl(Smem &sm, int blk, int warp, int lane, f2_t nz2) {
     constexpr int GS = Fmt<QT>::GS;
     const float lo = (float)Fmt<QT>::QMIN, hi = (float)Fmt<QT>::QMAX;
-    float w[16];
+    const int l8 = lane & 7, srow = warp * 4 + (lane >> 3);
+    f2_t pr[8];
 #pragma unroll
-    for (int s = 0; s < 16; ++s) w[s] = sm.Wt[wt_idx(srow, blk * 128 + s * 8 + q8)];
+    for (int m = 0; m < 8; ++m)
+        pr[m] = f2_pack(sm.Wt[wt_idx(srow, blk * 128 + 16 * m + l8)], sm.Wt[wt_idx(srow, blk * 128 + 16 * m + 8 + l8)]);
     const float d = sm.rs.d[srow], dm = sm.rs.dm[srow];
-    const float *Ud = sm.u.Ud;
+    const float *Ud = sm.u.Ud + l8 * 16;
+    const int sw = (l8 >> 1) & 3;
+    float *et = sm.Et + srow * 128, *wqo = sm.Wq + srow * 128;
+    uint8_t *cd = sm.codes + srow * 256 + blk * 128;
+    float sc = 0.0f, zz = 0.0f;
+    DivBy ds = DivBy::make(1.0f);
+    bool bad = false;
 #pragma unroll
     for (int s = 0; s < 16; ++s) {
-        const int g = (blk * 128 + s * 8) / GS;
-        const float sc = __fmul_rn(d, kq_code_to_f<QT>(sm.rs.sq[srow][g]));
-        const float zz = __fmul_rn(dm, kq_code_to_f<QT>(sm.rs.zq[srow][g]));
+        if ((8 * s) % GS == 0) {
+            const int g = (blk * 128 + 8 * s) / GS;
+            sc = __fmul_rn(d, kq_code_to_f<QT>(sm.rs.sq[srow][g]));
+            zz = __fmul_rn(dm, kq_code_to_f<QT>(sm.rs.zq[srow][g]));
+            ds = DivBy::make(fmaxf(sc, GQ_EPS));
+        }
 #pragma unroll 1
         for (int q = 0; q < 8; ++q) {
-            const int i = s * 8 + q;
-            const float x = __shfl_sync(0xffffffffu, w[s], q, 8);
-            const float qv = kq_quant(x, sc, zz, lo, hi);                       // :247-254
-            const float wq = kq_dequant(qv, sc, zz);                            // :255-261
-            const float err = __fdiv_rn(__fsub_rn(x, wq), Ud[i * 128 + i]);     // :264
-            if (q8 == q) {
-                sm.Et[srow * 128 + i] = err;                                    // :268
-                sm.codes[srow * 256 + blk * 128 + i] = (uint8_t)(int8_t)(int)qv;  // :263
-                sm.Wt[wt_idx(srow, blk * 128 + i)] = wq;                        // :266
-            }
-            const float *urow = Ud + i * 128 + q8;
+            const int i = 8 * s + q;
+            // loads that do not depend on the chain first: U[i, my columns], the diagonal's reciprocal
+            const float4 *urow = reinterpret_cast<const float4 *>(Ud + i * 128);
+            float4 u[4];
 #pragma unroll
-            for (int s2 = s; s2 < 16; ++s2) w[s2] = __fsub_rn(w[s2], __fmul_rn(err, urow[s2 * 8]));  // :267
+            for (int c4 = s >> 2; c4 < 4; ++c4) u[c4] = urow[c4 ^ sw];
+            DivBy du;
+            du.b = sm.dg_b[i];
+            du.y = sm.dg_y[i];
+            float plo, phi;
+            f2_unpack(pr[s >> 1], plo, phi);
+            const float x = __shfl_sync(0xffffffffu, (s & 1) ? phi : plo, q, 8);
+            const float t = __fadd_rn(x, zz);
+            const float qv = clampf(rintf(SAFE ? ds.div(t) : ds.div_fast(t, bad)), lo, hi);   // :247-254 (kq_quant)
+            const float wq = kq_dequant(qv, sc, zz);                                          // :255-261
+            const float num = __fsub_rn(x, wq);
+            const float err = SAFE ? du.div(num) : du.div_fast(num, bad);                     // :264
+            const f2_t e2 = f2_pack(err, err);
+#pragma unroll
+            for (int c4 = s >> 2; c4 < 4; ++c4) {                                             // :267
+                if (2 * c4 >= (s >> 1)) pr[2 * c4] = f2_sub(pr[2 * c4], f2_mul_nofuse(e2, f2_pack(u[c4].x, u[c4].y), nz2));
+                pr[2 * c4 + 1] = f2_sub(pr[2 * c4 + 1], f2_mul_nofuse(e2, f2_pack(u[c4].z, u[c4].w), nz2));
+            }
+            // outputs of column i: the owner lane stores, the others write to a per-lane dummy slot (no branch)
+            const bool own = (l8 == q);
+            float *ep = own ? et + i : sm.dummy_f + lane;
+            float *wp = own ? wqo + i : sm.dummy_f + 32 + lane;
+            uint8_t *cp = own ? cd + i : sm.dummy_b + lane;
+            *ep = err;                                                                        // :268
+            *wp = wq;                                                                         // :266
+            *cp = (uint8_t)(int8_t)(int)qv;                                                   // :263
         }
     }
+    return bad;
+}
+
+template <int QT>
+__device__ __forceinline__ void serial_block(Smem &sm, int blk, int warp, int lane, f2_t nz2) {
+    const bool bad = serial_block_impl<QT, false>(sm, blk, warp, lane, nz2);
+    if (__any_sync(0xffffffffu, bad)) serial_block_impl<QT, true>(sm, blk, warp, lane, nz2);   // rare: exact IEEE divisions
+    __syncwarp();
+    // the block's dequantised values replace the consumed columns of the tile (this warp's 4 rows)
+    const int srow = warp * 4 + (lane >> 3), l8 = lane & 7;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) sm.Wt[wt_idx(srow, blk * 128 + 8 * s + l8)] = sm.Wq[srow * 128 + 8 * s + l8];
 }
 
 template <int QT>
@@ -194,18 +263,25 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rg = warp >> 1, ch = warp & 1;            // rank-update mapping: rows 8rg..8rg+7, cols ch*128+4*lane..
-    const int srow = warp * 4 + (lane >> 3), q8 = lane & 7;  // serial mapping
     const int r0 = blockIdx.x * R;
     const int nsb = p.d_col / GQ_QK_K, ng = p.d_col / GS;
     const size_t ld = (size_t)p.d_col;
 
+    // Diagonal (128 x 128) block of U -> shared memory in the serial phase's permuted layout (ud_idx).  Row i only
+    // needs its columns j >= 32*(i/32) (the lanes read whole 16-byte chunks = 32-column spans at and right of the diagonal).
     auto load_Ud = [&](int c1) {
-#pragma unroll
-        for (int m = 0; m < 16; ++m) {
-            const int id = tid + NT * m, row = id >> 5, c16 = id & 31;
-            cp_async16(sm.u.Ud + row * 128 + 4 * c16, p.U + (size_t)(c1 + row) * ld + c1 + 4 * c16);
+        for (int id = tid; id < 128 * 128; id += NT) {
+            const int i = id >> 7, j = id & 127;
+            if (j >= (i & ~31)) cp_async4(sm.u.Ud + ud_idx(i, j), p.U + (size_t)(c1 + i) * ld + c1 + j);
         }
         cp_async_commit();
+    };
+    auto diag_recip = [&]() {      // after Ud has landed: checked reciprocals of the diagonal (off the dependent chain)
+        if (tid < 128) {
+            const DivBy dv = DivBy::make(sm.u.Ud[ud_idx(tid, tid)]);
+            sm.dg_b[tid] = dv.b;
+            sm.dg_y[tid] = dv.y;
+        }
     };
     auto store_E = [&](int c1) {   // errors of the block replace the consumed columns of W
 #pragma unroll
@@ -227,7 +303,6 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
             }
         }
     };
-
     PhaseClock pc(p.clk);
     for (int sb = p.sb_begin; sb < p.sb_end; ++sb) {
         const int c = sb * GQ_QK_K;
@@ -253,26 +328,28 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
         uint32_t vmask = 0, amask = 0;
         tile_search<QT, R, NT>(sm.Wt, sm.gsc, sm.gzr, p.sp, vmask, amask);
         publish_flags(p.flags ? p.flags + 2 * sb : nullptr, vmask, amask);
+        cp_async_wait<0>();
         __syncthreads();
         pc.lap(PH_SEARCH);
-        if (tid < R) {
-            tile_finalize_row<QT, R>(tid, sm.gsc, sm.gzr, sm.rs);
-            if (r0 + tid < p.d_row) {
-                const size_t gr = (size_t)(r0 + tid);
-                p.d[gr * nsb + sb] = sm.rs.dbits[tid];
-                p.dmin[gr * nsb + sb] = sm.rs.dmbits[tid];
+        diag_recip();
+        if (tid >= 128 && tid < 128 + R) {
+            const int row = tid - 128;
+            tile_finalize_row<QT, R>(row, sm.gsc, sm.gzr, sm.rs);
+            if (r0 + row < p.d_row) {
+                const size_t gr = (size_t)(r0 + row);
+                p.d[gr * nsb + sb] = sm.rs.dbits[row];
+                p.dmin[gr * nsb + sb] = sm.rs.dmbits[row];
 #pragma unroll
                 for (int g = 0; g < GPR; ++g) {
-                    p.sq[gr * ng + sb * GPR + g] = sm.rs.sq[tid][g];
-                    p.zq[gr * ng + sb * GPR + g] = sm.rs.zq[tid][g];
+                    p.sq[gr * ng + sb * GPR + g] = sm.rs.sq[row][g];
+                    p.zq[gr * ng + sb * GPR + g] = sm.rs.zq[row][g];
                 }
             }
         }
-        cp_async_wait<0>();
         __syncthreads();
         pc.lap(PH_FINAL);
 
-        serial_block<QT>(sm, 0, srow, q8);
+        serial_block<QT>(sm, 0, warp, lane, p.nz2);
         __syncthreads();
         pc.lap(PH_SERIAL0);
         store_E(c);
@@ -296,9 +373,11 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
         load_Ud(c + 128);
         cp_async_wait<0>();
         __syncthreads();
+        diag_recip();
+        __syncthreads();
         pc.lap(PH_MID);
 
-        serial_block<QT>(sm, 1, srow, q8);
+        serial_block<QT>(sm, 1, warp, lane, p.nz2);
         __syncthreads();
         pc.lap(PH_SERIAL1);
         store_E(c + 128);
@@ -455,6 +534,7 @@ extern "C" int gq_gptq_quantize(float *W, const float *U, int d_row, int d_col, 
     p.qweight = (uint8_t *)qweight; p.d = d; p.sq = (uint8_t *)sq; p.dmin = dmin; p.zq = (uint8_t *)zq;
     p.packed = packed; p.wdeq = wdeq; p.wdeq_dtype = wdeq_dtype; p.flags = search_flags;
     p.clk = g_phase_clk;
+    p.nz2 = F2_NEG_ZERO2;
     cudaStream_t st = (cudaStream_t)stream;
     switch (qtype) {
     case GQ_Q2_K: return run_layer<GQ_Q2_K>(p, mode, workspace, ws_bytes, st);

@@ -78,6 +78,11 @@ __global__ void reverse_copy_kernel(const float *__restrict__ H, float *A, int n
         A[i] = H[total - 1 - i];
 }
 
+// NOTE (round 1): three rewrites of this kernel were measured and discarded (profiles/r01_gptq_kernel_notes.md): a
+// two-level blocked version with a register/shuffle 32 x 32 factorisation (130-138 us: shuffles under `if (warp == 0)`
+// compile to WARPSYNC.COLLECTIVE sequences; run redundantly by all warps it executes 0.5 M warp instructions), and a
+// one-warp shared-memory version with rolled loops (200 us: every step pays the full shared-memory round trip).
+// This column sweep takes ~129 us per launch and remains the critical path of the chain at n = 4096.
 // Factor the (128 x 128) diagonal block at A[k0:k0+128, k0:k0+128] in shared memory: L_kk (written back to A)
 // and inv(L_kk) (written to Binv, the level-0 blocks of the triangular inverse; upper part zeroed).
 constexpr int DT = 1024;

@@ -93,16 +93,16 @@ inline EncodeTiledFn get_encode_fn() {
     return fn;
 }
 // 2D K-major tensor map: `rows` rows of `cols` elements (row pitch = cols * elem_bytes), box = (box_cols x box_rows),
-// 128-byte swizzle (box_cols * elem_bytes must be 128).
+// 128-byte swizzle by default (box_cols * elem_bytes must then be 128).
 inline bool make_map_2d(CUtensorMap *m, void *base, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols,
-                        uint32_t box_cols, uint32_t box_rows) {
+                        uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return false;
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {cols * (uint64_t)elem_bytes};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    return fn(m, dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    return fn(m, dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 inline int num_sms() {

@@ -267,12 +267,14 @@ class Quantizer:
         kw = self.quantizer_kwargs
         rank, world = _rank(), _world()
         on_gpu = next(iter(handles.values())).layer.weight.is_cuda
-        overlap = self.overlap_prepare and on_gpu and len(groups) > 1
+        overlap = bool(self.overlap_prepare) and on_gpu and len(groups) > 1
+        staged = overlap and self.overlap_prepare == "staged"
         main = torch.cuda.current_stream() if on_gpu else None
         # ---- phase A: per distinct Hessian: all-reduce, fp32 working copy, dead-channel fix, U = chol(inv(H)).
         # With `overlap_prepare` every group's Cholesky chain runs on its own side stream (own workspace slot), so
-        # the latency-bound chains of the 4 groups of a block run concurrently and hide behind the column-loop
-        # kernels of the groups before them; the main stream only waits for the U it is about to consume.
+        # the latency-bound chains of the 4 groups of a block run concurrently.  True / "eager": the main stream
+        # waits only for the U it is about to consume, so later chains also overlap the column-loop kernels of the
+        # groups before them; "staged": all chains first, then the column loops.
         plans = []
         for gi, names in enumerate(groups.values()):
             hs = [handles[n] for n in names]
@@ -295,8 +297,12 @@ class Quantizer:
                     done.record(side)
             plans.append((names, hs, rows, W, U, not_pd, done))
         # ---- phase B: the column loops, in module order, on the main stream
+        if staged:      # "staged": the column loops start only when every chain has finished (no SM contention)
+            for plan in plans:
+                if plan[6] is not None:
+                    main.wait_event(plan[6])
         for names, hs, rows, W, U, not_pd, done in plans:
-            if done is not None:
+            if done is not None and not staged:
                 main.wait_event(done)
             q_types = [quant_config.get(n.split(".")[-1], GGMLQuantizationType.Q4_K) for n in names]  # quantizer.py:249
             dtype = hs[0].layer.weight.dtype

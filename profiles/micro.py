@@ -55,6 +55,8 @@ def spd(n, dev="cuda"):
 
 def main():
     what = set(sys.argv[1:]) or {"prepare", "gptq", "hessian", "rtn"}
+    if "small" in what:
+        what.add("gptq")
     torch.manual_seed(0)
     if "prepare" in what:
         for n in (4096, 14336):
@@ -70,7 +72,10 @@ def main():
             mn, av = timed(lambda: ops.hessian_update(H, X, 0.5, 0.5), warm=1, it=3)
             print(f"hessian n={n} T={T}: {mn:.3f} ms  -> {2 * T * n * n / 2 / mn / 1e9:.0f} TFLOP/s (upper-triangle flops)", flush=True)
     if "gptq" in what:
-        for rows, n in ((6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336)):
+        shapes = ((6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336))
+        if "small" in what:      # fewer CTAs streaming the same U: probes L2 hot-line contention
+            shapes = ((256, 4096), (1024, 4096), (2048, 4096), (4096, 4096))
+        for rows, n in shapes:
             U = torch.triu(torch.randn(n, n, device="cuda") * 0.01) + torch.eye(n, device="cuda")
             W0 = torch.randn(rows, n, device="cuda") * 0.02
             mn, av = timed(lambda: ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16), warm=1, it=2)
