@@ -332,10 +332,12 @@ class Quantizer:
         del plans
 
     def _side_stream(self, i: int):
-        """Side streams for the Cholesky chains; earlier groups get the higher priority (their U is needed first)."""
+        """Side streams for the Cholesky chains.  They run at HIGH priority: their kernels are small and latency-bound,
+        the column-loop kernels on the main stream have hundreds of long-lived CTAs; with equal priorities a chain's
+        next kernel queues behind all pending column-loop CTAs and the chain starves."""
         while len(self._side_streams) <= i:
-            k = len(self._side_streams)
-            self._side_streams.append(torch.cuda.Stream(priority=-1 if k == 0 else 0))
+            lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
+            self._side_streams.append(torch.cuda.Stream(priority=hi))
         return self._side_streams[i]
 
     def _sharded_gptq(self, W, U, qt, dtype, rank, world):
