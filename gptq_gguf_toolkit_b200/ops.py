@@ -137,9 +137,12 @@ def prepare(H: torch.Tensor, W: torch.Tensor, rel_damp: float, stream: Optional[
 
 def gptq_quantize(W: torch.Tensor, U: torch.Tensor, q_type: int, block_size: int = 128, rmin: float = -1.0,
                   rdelta: float = 0.1, nstep: int = 20, mode: int = L.GQ_MODE_EXACT, packed: bool = True,
-                  wdeq_dtype: Optional[torch.dtype] = None, search_flags: bool = False):
+                  wdeq_dtype: Optional[torch.dtype] = None, search_flags: bool = False,
+                  stream: Optional["torch.cuda.Stream"] = None):
     """The column loop of one layer (gptq.py:146-295).  W: fp32 working copy, CLOBBERED.
-    Returns (qweight, d, sq, dmin, zq, packed|None, wdeq|None, flags|None)."""
+    Returns (qweight, d, sq, dmin, zq, packed|None, wdeq|None, flags|None).
+    stream: enqueue on this side stream (outputs are allocated on the CURRENT stream, which the side stream first
+    waits for; the caller waits on the side stream before consuming the results)."""
     L.require_cuda(W, U)
     assert W.dtype == torch.float32 and W.is_contiguous() and U.dtype == torch.float32 and U.is_contiguous()
     d_row, d_col = W.shape
@@ -147,12 +150,15 @@ def gptq_quantize(W: torch.Tensor, U: torch.Tensor, q_type: int, block_size: int
     flags = torch.zeros(d_col // QK_K, 2, dtype=torch.int32, device=W.device) if search_flags else None
     lib = L.load()
     nws = lib.gq_gptq_workspace_bytes(d_row, d_col, int(mode))
-    ws = _workspace(W.device, nws) if nws else None
-    with _span("gptq"):
-        L.check(lib.gq_gptq_quantize(
-            L.ptr(W), L.ptr(U), d_row, d_col, int(q_type), int(block_size), float(rmin), float(rdelta), int(nstep), int(mode),
-            L.ptr(qweight), L.ptr(d), L.ptr(sq), L.ptr(dmin), L.ptr(zq), L.ptr(pk), L.ptr(wd),
-            L.dtype_code(wdeq_dtype) if wdeq_dtype is not None else 0, L.ptr(flags), L.ptr(ws), nws, L.stream_of(W.device)))
+    ws = _workspace(W.device, nws, slot=100 if stream is not None else 0) if nws else None
+    if stream is not None:
+        stream.wait_stream(torch.cuda.current_stream(W.device))
+    with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
+        with _span("gptq"):
+            L.check(lib.gq_gptq_quantize(
+                L.ptr(W), L.ptr(U), d_row, d_col, int(q_type), int(block_size), float(rmin), float(rdelta), int(nstep), int(mode),
+                L.ptr(qweight), L.ptr(d), L.ptr(sq), L.ptr(dmin), L.ptr(zq), L.ptr(pk), L.ptr(wd),
+                L.dtype_code(wdeq_dtype) if wdeq_dtype is not None else 0, L.ptr(flags), L.ptr(ws), nws, L.stream_of(W.device)))
     return qweight, d, sq, dmin, zq, pk, wd, flags
 
 

@@ -118,7 +118,7 @@ class Quantizer:
                  # ---- additions over the reference ----
                  calibration_batch_size: int = 8, share_hessians: bool = True, keep_results: bool = False,
                  save_packed: bool = True, timer: Optional[PhaseTimer] = None, early_exit_pass1: bool = True,
-                 overlap_prepare: bool = True) -> None:
+                 overlap_prepare: bool = True, defer_last_layer: bool = True) -> None:
         self.model = model
         self.data_loader = data_loader
         self.quantizable_modules = quantizable_modules
@@ -138,6 +138,8 @@ class Quantizer:
         self.save_packed = save_packed
         self.early_exit_pass1 = early_exit_pass1
         self.overlap_prepare = overlap_prepare
+        self.defer_last_layer = defer_last_layer
+        self._split_ok: Optional[bool] = None
         self._side_streams: list = []
         self._mask_flags: list = []
         self.timer = timer or PhaseTimer(False)
@@ -255,12 +257,15 @@ class Quantizer:
                     state["last"] = order[-1]
             state["fired"] = 0
 
-        return handles, hooks, end_of_forward
+        return handles, hooks, end_of_forward, state
 
     # -------------------------------------------------------------------------------------------
-    def _quant_group(self, handles: Dict[str, GPTQ], quant_config):
+    def _quant_group(self, handles: Dict[str, GPTQ], quant_config, defer: Optional[str] = None):
         """quantizer.py:242-275.  Handles are processed per shared accumulator; same-q_type members of a group are
-        stacked row-wise into one launch, and with several ranks each rank takes a row slice."""
+        stacked row-wise into one launch, and with several ranks each rank takes a row slice.
+        defer: name of a layer whose (single-layer) group is NOT finished here: its Cholesky chain AND its column loop
+        are enqueued on the group's side stream and a callable is returned that, when called later on the main
+        stream, waits for them, swaps the layer's weight and emits the result (see _deferred_tail_plan)."""
         groups: Dict[int, List[str]] = {}
         for name, h in handles.items():
             groups.setdefault(id(h.hessian), []).append(name)
@@ -295,41 +300,68 @@ class Quantizer:
                 if side is not None:
                     done = torch.cuda.Event()
                     done.record(side)
-            plans.append((names, hs, rows, W, U, not_pd, done))
+            plans.append((names, hs, rows, W, U, not_pd, done, side))
+        deferred = None
+        if defer is not None:
+            hit = [pl for pl in plans if pl[0] == [defer]]
+            if overlap and world == 1 and len(hit) == 1 and hit[0][7] is not None:
+                deferred = hit[0]
+                plans = [pl for pl in plans if pl is not deferred]
         # ---- phase B: the column loops, in module order, on the main stream
         if staged:      # "staged": the column loops start only when every chain has finished (no SM contention)
             for plan in plans:
                 if plan[6] is not None:
                     main.wait_event(plan[6])
-        for names, hs, rows, W, U, not_pd, done in plans:
-            if done is not None and not staged:
-                main.wait_event(done)
-            q_types = [quant_config.get(n.split(".")[-1], GGMLQuantizationType.Q4_K) for n in names]  # quantizer.py:249
-            dtype = hs[0].layer.weight.dtype
-            # sub-groups of equal q_type, keeping module order
-            by_type: Dict[int, List[int]] = {}
-            for i, qt in enumerate(q_types):
-                by_type.setdefault(int(qt), []).append(i)
-            offs = [0]
-            for r in rows:
-                offs.append(offs[-1] + r)
-            for qt, idxs in by_type.items():
-                self._log(f"Quantizing {[names[i] for i in idxs]} with {GGMLQuantizationType(qt).name}.")
-                Wg = W if len(idxs) == len(hs) else torch.cat([W[offs[i]:offs[i + 1]] for i in idxs], 0).contiguous()
-                outs = self._sharded_gptq(Wg, U, qt, dtype, rank, world)
-                qweight, d, sq, dmin, zq, packed, wdeq = outs
-                r0 = 0
-                for i in idxs:
-                    r1 = r0 + rows[i]
-                    h = hs[i]
-                    h.layer.weight.data = wdeq[r0:r1].clone() if len(idxs) > 1 else wdeq[r0:r1]   # quantizer.py:257-264
-                    self._emit(names[i], qt, (qweight[r0:r1], d[r0:r1], sq[r0:r1], dmin[r0:r1], zq[r0:r1]),
-                               packed[r0:r1] if packed is not None else None)
-                    r0 = r1
-            self._not_pd_flags.append((names, not_pd))
-            for h in hs:
-                h.reset()                                                      # quantizer.py:265
-        del plans
+        for plan in plans:
+            if plan[6] is not None and not staged:
+                main.wait_event(plan[6])
+            self._finish_group(plan, self._launch_group(plan, quant_config, rank, world, None))
+        if deferred is None:
+            return None
+        # the deferred group: column loop on ITS side stream, right behind its Cholesky chain
+        launched = self._launch_group(deferred, quant_config, rank, world, deferred[7])
+        ready = torch.cuda.Event()
+        ready.record(deferred[7])
+
+        def finish():
+            main.wait_event(ready)
+            self._finish_group(deferred, launched)
+        return finish
+
+    def _launch_group(self, plan, quant_config, rank, world, stream):
+        """Column loops of one group (one launch per q_type present in it); results are not consumed yet."""
+        names, hs, rows, W, U = plan[:5]
+        q_types = [quant_config.get(n.split(".")[-1], GGMLQuantizationType.Q4_K) for n in names]  # quantizer.py:249
+        dtype = hs[0].layer.weight.dtype
+        by_type: Dict[int, List[int]] = {}          # sub-groups of equal q_type, keeping module order
+        for i, qt in enumerate(q_types):
+            by_type.setdefault(int(qt), []).append(i)
+        offs = [0]
+        for r in rows:
+            offs.append(offs[-1] + r)
+        launched = []
+        for qt, idxs in by_type.items():
+            self._log(f"Quantizing {[names[i] for i in idxs]} with {GGMLQuantizationType(qt).name}.")
+            Wg = W if len(idxs) == len(hs) else torch.cat([W[offs[i]:offs[i + 1]] for i in idxs], 0).contiguous()
+            launched.append((qt, idxs, self._sharded_gptq(Wg, U, qt, dtype, rank, world, stream)))
+        return launched
+
+    def _finish_group(self, plan, launched):
+        """Write the dequantised weights back into the layers (quantizer.py:257-264), emit data.pth, reset handles."""
+        names, hs, rows, W, U, not_pd = plan[:6]
+        for qt, idxs, outs in launched:
+            qweight, d, sq, dmin, zq, packed, wdeq = outs
+            r0 = 0
+            for i in idxs:
+                r1 = r0 + rows[i]
+                h = hs[i]
+                h.layer.weight.data = wdeq[r0:r1].clone() if len(idxs) > 1 else wdeq[r0:r1]
+                self._emit(names[i], qt, (qweight[r0:r1], d[r0:r1], sq[r0:r1], dmin[r0:r1], zq[r0:r1]),
+                           packed[r0:r1] if packed is not None else None)
+                r0 = r1
+        self._not_pd_flags.append((names, not_pd))
+        for h in hs:
+            h.reset()                                                          # quantizer.py:265
 
     def _side_stream(self, i: int):
         """Side streams for the Cholesky chains.  They run at HIGH priority: their kernels are small and latency-bound,
@@ -340,13 +372,13 @@ class Quantizer:
             self._side_streams.append(torch.cuda.Stream(priority=hi))
         return self._side_streams[i]
 
-    def _sharded_gptq(self, W, U, qt, dtype, rank, world):
+    def _sharded_gptq(self, W, U, qt, dtype, rank, world, stream=None):
         kw = self.quantizer_kwargs
         args = dict(block_size=kw.get("block_size", 128) or W.shape[1], rmin=kw.get("rmin", -1.0),
                     rdelta=kw.get("rdelta", 0.1), nstep=kw.get("nstep", 20), packed=True, wdeq_dtype=dtype,
                     mode={"exact": 0, "fast": 1}[kw.get("mode", "exact")])
         if world == 1:
-            return ops.gptq_quantize(W, U, qt, **args)[:7]
+            return ops.gptq_quantize(W, U, qt, stream=stream, **args)[:7]
         total = W.shape[0]
         per = -(-total // world)
         per = -(-per // 32) * 32                     # row slices in units of the kernel's 32-row CTA tile
@@ -361,6 +393,65 @@ class Quantizer:
                 dist.all_gather_into_tensor(g, t.contiguous())
                 full.append(g[:total])
         return tuple(full)
+
+    # -------------------------------------------------------------------------------------------
+    def _deferred_tail_plan(self, block, layers, hook_state, batches, device):
+        """Can pass 2 of this block be split at its last quantised layer (out = residual + last(x))?
+
+        Pre-norm decoder blocks (Llama family) end with `hidden = residual + mlp(norm(hidden))` where the MLP's last
+        operation is the last quantised layer (down_proj) and `residual` is the input of `post_attention_layernorm`.
+        That structure is not assumed but CHECKED once, on the first calibration batch of the first block: the output
+        of the plain `block(...)` call must equal `residual + last(x)` bit for bit, otherwise the generic path is kept."""
+        if not (self.defer_last_layer and self.overlap_prepare and _world() == 1 and not self.cpu_offload_activations):
+            return None
+        last_name = hook_state.get("last")
+        norm = getattr(block, "post_attention_layernorm", None)
+        if last_name is None or not isinstance(norm, nn.Module) or not next(block.parameters()).is_cuda:
+            return None
+        if not all(len(a) == 1 and isinstance(a[0], torch.Tensor) for a, _ in batches):
+            return None
+        plan = {"last_name": last_name, "last": layers[last_name], "norm": norm}
+        if self._split_ok is None:
+            inp_args, inp_kwargs = batches[0]
+            cap = {}
+            h1 = norm.register_forward_pre_hook(lambda m, a: cap.__setitem__("res", a[0]))
+            h2 = plan["last"].register_forward_pre_hook(lambda m, a: cap.__setitem__("din", a[0]))
+            try:
+                full = maybe_first_element(block(*to(inp_args, device=device), **to(inp_kwargs, device=device)))
+            finally:
+                h1.remove(); h2.remove()
+            ok = "res" in cap and "din" in cap and full.shape == cap["res"].shape
+            if ok:
+                ok = bool(torch.equal(full, cap["res"] + plan["last"](cap["din"])))
+            self._split_ok = ok
+            self._log(f"deferred-tail split of pass 2 at {last_name}: {'enabled' if ok else 'not applicable'}")
+        return plan if self._split_ok else None
+
+    def _split_fronts(self, block, tail, batches, device):
+        """Run the block up to (not including) its last quantised layer for every batch; returns [(residual, x)]."""
+        cap = {}
+
+        def grab_res(_, a):
+            cap["res"] = a[0]
+
+        def grab_din(_, a):
+            cap["din"] = a[0]
+            raise ForwardInterrupt
+
+        h1 = tail["norm"].register_forward_pre_hook(grab_res)
+        h2 = tail["last"].register_forward_pre_hook(grab_din)
+        fronts = []
+        try:
+            with self.timer.span("forward2"):
+                for inp_args, inp_kwargs in batches:
+                    try:
+                        block(*to(inp_args, device=device), **to(inp_kwargs, device=device))
+                    except ForwardInterrupt:
+                        pass
+                    fronts.append((cap.pop("res"), cap.pop("din")))
+        finally:
+            h1.remove(); h2.remove()
+        return fronts
 
     # -------------------------------------------------------------------------------------------
     def _batched_inputs(self, input_args, input_kwargs):
@@ -447,7 +538,7 @@ class Quantizer:
             block = block.to(device)
             layer_prefix = f"{self.block_modules}.{block_id}."
             layers = select_layers(self.model, layer_prefix, self.quantizable_modules, LINEAR_LAYERS)
-            handles, hooks, end_of_forward = self._prepare_hooks_and_handles(layers)
+            handles, hooks, end_of_forward, hook_state = self._prepare_hooks_and_handles(layers)
 
             with self.timer.span("forward1"):
                 for inp_args, inp_kwargs in batches:
@@ -459,23 +550,37 @@ class Quantizer:
             for h in hooks.values():
                 h.remove()
 
-            self._quant_group(handles, quant_config)
+            tail = self._deferred_tail_plan(block, layers, hook_state, batches, device)
+            finish = self._quant_group(handles, quant_config, defer=tail["last_name"] if tail else None)
 
-            with self.timer.span("forward2"):
-                for inp_args, inp_kwargs in batches:
-                    out = block(*to(inp_args, device=device), **to(inp_kwargs, device=device))
-                    out = maybe_first_element(out)
-                    if self.cpu_offload_activations:
-                        out = out.cpu()
-                    if len(inp_args) > 0:                                     # quantizer.py:167-168
-                        if inp_args[0].shape == out.shape and inp_args[0].device == out.device:
-                            inp_args[0].copy_(out)      # in place: batches are views of one activation buffer
+            if finish is None:
+                with self.timer.span("forward2"):
+                    for inp_args, inp_kwargs in batches:
+                        out = block(*to(inp_args, device=device), **to(inp_kwargs, device=device))
+                        out = maybe_first_element(out)
+                        if self.cpu_offload_activations:
+                            out = out.cpu()
+                        if len(inp_args) > 0:                                     # quantizer.py:167-168
+                            if inp_args[0].shape == out.shape and inp_args[0].device == out.device:
+                                inp_args[0].copy_(out)      # in place: batches are views of one activation buffer
+                            else:
+                                inp_args[0] = out
+                        elif "hidden_states" in inp_kwargs:
+                            inp_kwargs["hidden_states"] = out
                         else:
-                            inp_args[0] = out
-                    elif "hidden_states" in inp_kwargs:
-                        inp_kwargs["hidden_states"] = out
-                    else:
-                        raise ValueError("Unsupported block input format.")
+                            raise ValueError("Unsupported block input format.")
+            else:
+                # Pass 2, split at the block's last quantised layer: everything BEFORE it runs for all calibration
+                # batches while that layer's Cholesky chain and column loop are still in flight on a side stream
+                # (the block forwards are streams of short kernels, so the latency-bound chain interleaves with
+                # them instead of idling the GPU); then the layer itself + the residual add for all batches.
+                fronts = self._split_fronts(block, tail, batches, device)
+                finish()
+                with self.timer.span("forward2"):
+                    for (inp_args, _), (res, din) in zip(batches, fronts):
+                        out = res + tail["last"](din)
+                        inp_args[0].copy_(out)
+                del fronts
             if self.cpu_offload_modules:
                 block = block.cpu()
             del handles, hooks

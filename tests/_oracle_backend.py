@@ -46,7 +46,7 @@ def prepare(H, W, rel_damp, stream=None, slot=0):
     return torch.from_numpy(U), torch.tensor([int(bad)], dtype=torch.int32)
 
 
-def gptq_quantize(W, U, q_type, block_size=128, rmin=-1.0, rdelta=0.1, nstep=20, mode=0, packed=True,
+def gptq_quantize(W, U, q_type, block_size=128, rmin=-1.0, rdelta=0.1, nstep=20, mode=0, packed=True, stream=None,
                   wdeq_dtype=None, search_flags=False):
     out = orc.gptq_step(_np(W), _np(U), int(q_type), block_size, rmin, rdelta, nstep)
     five = _five_t(out[:5])
