@@ -361,7 +361,9 @@ def main():
         achieved = (rk_flops / world) / t_gptq / 1e12 if t_gptq > 0 else 0.0
         roofline = {
             "bound": "tensor", "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s",
-            "frac": achieved / pk["tf"], "traffic": None,
+            "frac": achieved / pk["tf"],
+            # ncu --set full, o_proj instance (4096 x 4096): dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_ncu_summary.md)
+            "traffic": 180.8e6, "traffic_note": "per launch of the 4096x4096 (o_proj) instance; algorithmic 217 MB (W fp32 in, upper U, codes, GGUF bytes, bf16 weights, errors out)",
             "kernel": "gptq_layer_kernel<Q4_K>: fused scale search + 128-step column loop + left-looking rank-k update + GGUF pack",
             "launches_per_step": n_layer_launch, "avg_launch_ms": 1e3 * t_gptq / max(1, n_layer_launch),
             "peak_source": pk["source"],
