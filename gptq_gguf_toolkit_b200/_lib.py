@@ -39,6 +39,7 @@ SIGNATURES = {
     "gq_prepare": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp, _sz, _vp, _vp]),
     "gq_gptq_workspace_bytes": (_sz, [_i, _i, _i]),
     "gq_gptq_quantize": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "gq_gptq_quantize_ex": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _d, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "gq_profile_enable": (None, [_i]),
     "gq_profile_read": (_i, [C.POINTER(_f), C.POINTER(_i)]),
     "gq_rtn_quantize": (_i, [_vp, _i, _i, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),

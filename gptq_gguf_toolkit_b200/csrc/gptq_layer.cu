@@ -45,6 +45,12 @@ struct LayerParams {
     int sb_begin, sb_end, fast;
     float *e_hi, *e_lo;     // (rows padded to 128) x 256, only in fast mode
     f2_t nz2;                  // {-0.0f, -0.0f}, deliberately a run-time value (see f2_mul_nofuse)
+    // static_groups (gptq.py:184-196): d/dmin/sq/zq already hold the scales of EVERY super-block (searched on the
+    // original W), the kernel only reads them.  perm (act_order, gptq.py:209-216; needs static_scales): W and U are in
+    // permuted column order, loop column c is original column perm[c] and uses that column's group (:233-238);
+    // qweight comes out in loop order, the fused pack / dequantised outputs are not available.
+    int static_scales;
+    const int *perm;
     unsigned long long *clk;   // optional (gq_debug_phase_clocks): 8 per-phase cycle counters summed over CTAs
 };
 
@@ -78,6 +84,9 @@ struct __align__(16) Smem {
     float gzr[R * 16];
     float dg_b[128];                         // diagonal of the current U block and its checked reciprocal (DivBy)
     float dg_y[128];
+    float pc_sc[R * 128];                    // act_order: per (row, column of the block) scale, zero, checked 1/scale
+    float pc_zz[R * 128];
+    float pc_y[R * 128];
     float dummy_f[64];                       // sink of the non-owner lanes' stores in the serial phase
     uint8_t dummy_b[32];
     RowScales<R> rs;
@@ -182,7 +191,7 @@ __device__ __forceinline__ void rank_update(float (&w)[8][4], const LayerParams 
 // block with SAFE = true (IEEE fallback inside DivBy::div).  The block's initial values are read from Wt, its
 // dequantised values go to `Wq` (a separate buffer), so a rerun starts from unchanged inputs.
 template <int QT, bool SAFE>
-__device__ __noinline__ bool serial_block_impl(Smem &sm, int blk, int warp, int lane, f2_t nz2) {
+__device__ __noinline__ bool serial_block_impl(Smem &sm, int blk, int warp, int lane, f2_t nz2, bool per_col) {
     constexpr int GS = Fmt<QT>::GS;
     const float lo = (float)Fmt<QT>::QMIN, hi = (float)Fmt<QT>::QMAX;
     const int l8 = lane & 7, srow = warp * 4 + (lane >> 3);
@@ -200,7 +209,7 @@ __device__ __noinline__ bool serial_block_impl(Smem &sm, int blk, int warp, int 
     bool bad = false;
 #pragma unroll
     for (int s = 0; s < 16; ++s) {
-        if ((8 * s) % GS == 0) {
+        if (!per_col && (8 * s) % GS == 0) {
             const int g = (blk * 128 + 8 * s) / GS;
             sc = __fmul_rn(d, kq_code_to_f<QT>(sm.rs.sq[srow][g]));
             zz = __fmul_rn(dm, kq_code_to_f<QT>(sm.rs.zq[srow][g]));
@@ -217,6 +226,12 @@ __device__ __noinline__ bool serial_block_impl(Smem &sm, int blk, int warp, int 
             DivBy du;
             du.b = sm.dg_b[i];
             du.y = sm.dg_y[i];
+            if (per_col) {          // act_order: every column has its own group (gptq.py:233-238)
+                sc = sm.pc_sc[srow * 128 + i];
+                zz = sm.pc_zz[srow * 128 + i];
+                ds.b = fmaxf(sc, GQ_EPS);
+                ds.y = sm.pc_y[srow * 128 + i];
+            }
             float plo, phi;
             f2_unpack(pr[s >> 1], plo, phi);
             const float x = __shfl_sync(0xffffffffu, (s & 1) ? phi : plo, q, 8);
@@ -245,9 +260,9 @@ __device__ __noinline__ bool serial_block_impl(Smem &sm, int blk, int warp, int 
 }
 
 template <int QT>
-__device__ __forceinline__ void serial_block(Smem &sm, int blk, int warp, int lane, f2_t nz2) {
-    const bool bad = serial_block_impl<QT, false>(sm, blk, warp, lane, nz2);
-    if (__any_sync(0xffffffffu, bad)) serial_block_impl<QT, true>(sm, blk, warp, lane, nz2);   // rare: exact IEEE divisions
+__device__ __forceinline__ void serial_block(Smem &sm, int blk, int warp, int lane, f2_t nz2, bool per_col) {
+    const bool bad = serial_block_impl<QT, false>(sm, blk, warp, lane, nz2, per_col);
+    if (__any_sync(0xffffffffu, bad)) serial_block_impl<QT, true>(sm, blk, warp, lane, nz2, per_col);   // rare: exact IEEE divisions
     __syncwarp();
     // the block's dequantised values replace the consumed columns of the tile (this warp's 4 rows)
     const int srow = warp * 4 + (lane >> 3), l8 = lane & 7;
@@ -303,6 +318,21 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
             }
         }
     };
+    auto per_column_tables = [&](int c1) {      // act_order: scale / zero / checked reciprocal of every (row, column) of a block
+        for (int id = tid; id < R * 128; id += NT) {
+            const int row = id >> 7, i = id & 127;
+            const int ocol = p.perm[c1 + i];
+            const size_t gr = (size_t)min(r0 + row, p.d_row - 1);
+            const float dd = __half2float(__ushort_as_half(p.d[gr * nsb + (ocol >> 8)]));
+            const float dm = __half2float(__ushort_as_half(p.dmin[gr * nsb + (ocol >> 8)]));
+            const float sc = __fmul_rn(dd, kq_code_to_f<QT>(p.sq[gr * ng + ocol / GS]));
+            const float zz = __fmul_rn(dm, kq_code_to_f<QT>(p.zq[gr * ng + ocol / GS]));
+            sm.pc_sc[id] = sc;
+            sm.pc_zz[id] = zz;
+            sm.pc_y[id] = DivBy::make(fmaxf(sc, GQ_EPS)).y;
+        }
+    };
+    const bool per_col = p.perm != nullptr;
     PhaseClock pc(p.clk);
     for (int sb = p.sb_begin; sb < p.sb_end; ++sb) {
         const int c = sb * GQ_QK_K;
@@ -325,31 +355,46 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
         // scale / min search on the live tile (gptq.py:240-245 -> quant_utils.py:90-145); U's diagonal
         // block for the first 128 columns streams in underneath it.
         load_Ud(c);
-        uint32_t vmask = 0, amask = 0;
-        tile_search<QT, R, NT>(sm.Wt, sm.gsc, sm.gzr, p.sp, vmask, amask);
-        publish_flags(p.flags ? p.flags + 2 * sb : nullptr, vmask, amask);
+        if (!p.static_scales) {
+            uint32_t vmask = 0, amask = 0;
+            tile_search<QT, R, NT>(sm.Wt, sm.gsc, sm.gzr, p.sp, vmask, amask);
+            publish_flags(p.flags ? p.flags + 2 * sb : nullptr, vmask, amask);
+        }
         cp_async_wait<0>();
         __syncthreads();
         pc.lap(PH_SEARCH);
         diag_recip();
         if (tid >= 128 && tid < 128 + R) {
             const int row = tid - 128;
-            tile_finalize_row<QT, R>(row, sm.gsc, sm.gzr, sm.rs);
-            if (r0 + row < p.d_row) {
-                const size_t gr = (size_t)(r0 + row);
-                p.d[gr * nsb + sb] = sm.rs.dbits[row];
-                p.dmin[gr * nsb + sb] = sm.rs.dmbits[row];
+            const size_t gr = (size_t)min(r0 + row, p.d_row - 1);
+            if (!p.static_scales) {
+                tile_finalize_row<QT, R>(row, sm.gsc, sm.gzr, sm.rs);
+                if (r0 + row < p.d_row) {
+                    p.d[gr * nsb + sb] = sm.rs.dbits[row];
+                    p.dmin[gr * nsb + sb] = sm.rs.dmbits[row];
+#pragma unroll
+                    for (int g = 0; g < GPR; ++g) {
+                        p.sq[gr * ng + sb * GPR + g] = sm.rs.sq[row][g];
+                        p.zq[gr * ng + sb * GPR + g] = sm.rs.zq[row][g];
+                    }
+                }
+            } else if (p.perm == nullptr) {       // static_groups: this super-block's scales were searched up front
+                sm.rs.dbits[row] = p.d[gr * nsb + sb];
+                sm.rs.dmbits[row] = p.dmin[gr * nsb + sb];
+                sm.rs.d[row] = __half2float(__ushort_as_half(sm.rs.dbits[row]));
+                sm.rs.dm[row] = __half2float(__ushort_as_half(sm.rs.dmbits[row]));
 #pragma unroll
                 for (int g = 0; g < GPR; ++g) {
-                    p.sq[gr * ng + sb * GPR + g] = sm.rs.sq[row][g];
-                    p.zq[gr * ng + sb * GPR + g] = sm.rs.zq[row][g];
+                    sm.rs.sq[row][g] = p.sq[gr * ng + sb * GPR + g];
+                    sm.rs.zq[row][g] = p.zq[gr * ng + sb * GPR + g];
                 }
             }
         }
+        if (p.perm != nullptr) per_column_tables(c);
         __syncthreads();
         pc.lap(PH_FINAL);
 
-        serial_block<QT>(sm, 0, warp, lane, p.nz2);
+        serial_block<QT>(sm, 0, warp, lane, p.nz2, per_col);
         __syncthreads();
         pc.lap(PH_SERIAL0);
         store_E(c);
@@ -374,10 +419,11 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
         cp_async_wait<0>();
         __syncthreads();
         diag_recip();
+        if (per_col) per_column_tables(c + 128);
         __syncthreads();
         pc.lap(PH_MID);
 
-        serial_block<QT>(sm, 1, warp, lane, p.nz2);
+        serial_block<QT>(sm, 1, warp, lane, p.nz2, per_col);
         __syncthreads();
         pc.lap(PH_SERIAL1);
         store_E(c + 128);
@@ -511,10 +557,13 @@ extern "C" size_t gq_gptq_workspace_bytes(int d_row, int d_col, int mode) {
     return mode == GQ_MODE_FAST ? fast_ws_bytes(d_row, d_col) : 0;
 }
 
-extern "C" int gq_gptq_quantize(float *W, const float *U, int d_row, int d_col, int qtype, int block_size,
-                                double rmin, double rdelta, int nstep, int mode, void *qweight, uint16_t *d,
-                                void *sq, uint16_t *dmin, void *zq, uint8_t *packed, void *wdeq, int wdeq_dtype,
-                                uint32_t *search_flags, void *workspace, size_t ws_bytes, gq_stream_t stream) {
+int gq_search_all_superblocks(const float *W, int d_row, int d_col, int qtype, double rmin, double rdelta, int nstep,
+                              uint16_t *d, uint16_t *dmin, void *sq, void *zq, uint32_t *search_flags, cudaStream_t st);
+
+extern "C" int gq_gptq_quantize_ex(float *W, const float *U, int d_row, int d_col, int qtype, int block_size,
+                                   double rmin, double rdelta, int nstep, int mode, int static_groups, const int *perm,
+                                   void *qweight, uint16_t *d, void *sq, uint16_t *dmin, void *zq, uint8_t *packed, void *wdeq,
+                                   int wdeq_dtype, uint32_t *search_flags, void *workspace, size_t ws_bytes, gq_stream_t stream) {
     FmtInfo f;
     GQ_REQUIRE(gq_fmt_info(qtype, f), "gq_gptq_quantize: unknown q_type %d", qtype);
     GQ_REQUIRE(W && U && qweight && d && sq && dmin && zq, "gq_gptq_quantize: null pointer");
@@ -528,6 +577,21 @@ extern "C" int gq_gptq_quantize(float *W, const float *U, int d_row, int d_col, 
         return GQ_ERR_UNSUPPORTED;
     }
     GQ_REQUIRE(mode == GQ_MODE_EXACT || mode == GQ_MODE_FAST, "gq_gptq_quantize: unknown mode %d", mode);
+    GQ_REQUIRE(static_groups >= 0 && static_groups <= 2, "gq_gptq_quantize: static_groups=%d must be 0, 1 or 2", static_groups);
+    if (qtype == GQ_Q3_K) { static_groups = 0; perm = nullptr; }      // gptq.py:204-206: Q3_K ignores both options
+    GQ_REQUIRE(perm == nullptr || static_groups == 2,
+               "gq_gptq_quantize: act_order (perm) needs static_groups = 2 (scales searched on the un-permuted W beforehand)");
+    GQ_REQUIRE(perm == nullptr || (packed == nullptr && wdeq == nullptr),
+               "gq_gptq_quantize: with perm the codes come out in loop order; pack / dequantise after un-permuting them");
+    if ((static_groups || perm) && mode != GQ_MODE_EXACT) {
+        gq_set_error("gq_gptq_quantize: static_groups / act_order are implemented for GQ_MODE_EXACT only");
+        return GQ_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (static_groups == 1) {     // gptq.py:184-196: all scales / zeros up front, on the weights as they are now
+        const int rc = gq_search_all_superblocks(W, d_row, d_col, qtype, rmin, rdelta, nstep, d, dmin, sq, zq, search_flags, st);
+        if (rc) return rc;
+    }
     LayerParams p;
     p.W = W; p.U = U; p.d_row = d_row; p.d_col = d_col;
     gq_fill_search_params(p.sp, (1 << f.bits) - 1, rmin, rdelta, nstep);
@@ -535,7 +599,7 @@ extern "C" int gq_gptq_quantize(float *W, const float *U, int d_row, int d_col, 
     p.packed = packed; p.wdeq = wdeq; p.wdeq_dtype = wdeq_dtype; p.flags = search_flags;
     p.clk = g_phase_clk;
     p.nz2 = F2_NEG_ZERO2;
-    cudaStream_t st = (cudaStream_t)stream;
+    p.static_scales = static_groups != 0; p.perm = perm;
     switch (qtype) {
     case GQ_Q2_K: return run_layer<GQ_Q2_K>(p, mode, workspace, ws_bytes, st);
     case GQ_Q3_K: return run_layer<GQ_Q3_K>(p, mode, workspace, ws_bytes, st);
@@ -543,4 +607,12 @@ extern "C" int gq_gptq_quantize(float *W, const float *U, int d_row, int d_col, 
     case GQ_Q5_K: return run_layer<GQ_Q5_K>(p, mode, workspace, ws_bytes, st);
     default: return run_layer<GQ_Q6_K>(p, mode, workspace, ws_bytes, st);
     }
+}
+
+extern "C" int gq_gptq_quantize(float *W, const float *U, int d_row, int d_col, int qtype, int block_size,
+                                double rmin, double rdelta, int nstep, int mode, void *qweight, uint16_t *d,
+                                void *sq, uint16_t *dmin, void *zq, uint8_t *packed, void *wdeq, int wdeq_dtype,
+                                uint32_t *search_flags, void *workspace, size_t ws_bytes, gq_stream_t stream) {
+    return gq_gptq_quantize_ex(W, U, d_row, d_col, qtype, block_size, rmin, rdelta, nstep, mode, 0, nullptr, qweight, d, sq, dmin,
+                               zq, packed, wdeq, wdeq_dtype, search_flags, workspace, ws_bytes, stream);
 }

@@ -197,6 +197,21 @@ extern "C" int gq_get_scale_and_zero(const float *x, long x_stride, int rows, in
     return dispatch_rtn(qtype, p, (cudaStream_t)stream);
 }
 
+// Scales / zeros of EVERY super-block of a (d_row, d_col) fp32 matrix in one launch -- GPTQ.step's static_groups
+// initialisation (gptq.py:184-196).  Internal (used by gq_gptq_quantize_ex); same outputs as d_col/256 calls of
+// gq_get_scale_and_zero on the 256-column slabs.
+int gq_search_all_superblocks(const float *W, int d_row, int d_col, int qtype, double rmin, double rdelta, int nstep,
+                              uint16_t *d, uint16_t *dmin, void *sq, void *zq, uint32_t *search_flags, cudaStream_t st) {
+    FmtInfo f;
+    GQ_REQUIRE(gq_fmt_info(qtype, f), "static_groups: unknown q_type %d", qtype);
+    RtnParams p;
+    p.W = W; p.w_dtype = GQ_F32; p.ld_in = d_col; p.d_row = d_row; p.nsb = d_col / GQ_QK_K;
+    gq_fill_search_params(p.sp, (1 << f.bits) - 1, rmin, rdelta, nstep);
+    p.d = d; p.dmin = dmin; p.d_stride = p.nsb; p.sq = (uint8_t *)sq; p.zq = (uint8_t *)zq; p.sq_stride = d_col / f.gs;
+    p.qweight = nullptr; p.packed = nullptr; p.wdeq = nullptr; p.wdeq_dtype = GQ_F32; p.flags = search_flags;
+    return dispatch_rtn(qtype, p, st);
+}
+
 extern "C" int gq_dequantize(int qtype, const void *qweight, const uint16_t *d, const void *sq, const uint16_t *dmin,
                              const void *zq, int d_row, int d_col, void *out, int out_dtype, gq_stream_t stream) {
     FmtInfo f;

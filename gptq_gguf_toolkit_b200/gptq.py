@@ -34,6 +34,8 @@ class HessianAccumulator:
         self.H: Optional[torch.Tensor] = None
         self.num_samples = 0
         self.U: Optional[torch.Tensor] = None          # filled by prepare(); shared by the handles
+        self.perm: Optional[torch.Tensor] = None       # act_order: argsort(diag H, descending) (gptq.py:210)
+        self.U_perm: Optional[torch.Tensor] = None     # ... and the factor of H[perm][:, perm]
         self.not_pd: Optional[torch.Tensor] = None
         self.dead: Optional[torch.Tensor] = None       # diag(H) == 0 before the dead-channel fix
         self.zero_cols: Optional[torch.Tensor] = None  # all-zero weight columns U was built for
@@ -62,6 +64,7 @@ class HessianAccumulator:
 
     def reset(self) -> None:
         self.H, self.U, self.not_pd, self.dead, self.zero_cols = None, None, None, None, None
+        self.perm, self.U_perm = None, None
         self.num_samples = 0
         self.synced = False
 
@@ -74,8 +77,6 @@ class GPTQ:
         if act_order:
             assert static_groups                                            # gptq.py:45-46
         assert isinstance(layer, nn.Linear), "libgq GPTQ supports nn.Linear layers"
-        if act_order or static_groups:
-            raise NotImplementedError("act_order / static_groups are not implemented in libgq yet (run_quant.sh leaves them off)")
         self.layer = layer
         self.W = self.layer.weight
         self.d_row, self.d_col = layer.weight.shape
@@ -146,12 +147,31 @@ class GPTQ:
         return self.hessian.U
 
     @torch.no_grad()
+    def _prepare_act_order(self):
+        """gptq.py:209-216: perm = argsort(diag H, descending); the loop runs on W[:, perm] with the factor of
+        H[perm][:, perm].  Shared by the handles attached to the same accumulator (same H => same perm)."""
+        hs = self.hessian
+        if hs.perm is None:
+            hs.perm = torch.argsort(torch.diag(hs.H), descending=True)
+            Hp = hs.H.index_select(0, hs.perm).index_select(1, hs.perm).contiguous()
+            hs.U_perm, hs.not_pd = ops.prepare(Hp, self.W.index_select(1, hs.perm).contiguous(), self.rel_damp)
+        self.not_pd = hs.not_pd
+        return hs.perm, hs.U_perm
+
+    @torch.no_grad()
     def step(self, q_type: GGMLQuantizationType):
         """gptq.py:146-295."""
         q_type = GGMLQuantizationType(int(q_type))
-        U = self._prepare()
+        if q_type == GGMLQuantizationType.Q3_K:             # gptq.py:204-206 (the reference switches them off for good)
+            self.act_order = False
+            self.static_groups = False
+        perm = None
+        if self.act_order:
+            perm, U = self._prepare_act_order()
+        else:
+            U = self._prepare()
         out = ops.gptq_quantize(self.W, U, int(q_type), self.block_size, self.rmin, self.rdelta, self.nstep,
-                                self.mode, packed=True, wdeq_dtype=self.W_dtype)
+                                self.mode, packed=True, wdeq_dtype=self.W_dtype, static_groups=self.static_groups, perm=perm)
         qweight, d, sq, dmin, zq, self.packed, self.wdeq, _ = out
         self.W = None   # the working copy was consumed by the kernel
         return qweight, d, sq, dmin, zq

@@ -138,15 +138,23 @@ def prepare(H: torch.Tensor, W: torch.Tensor, rel_damp: float, stream: Optional[
 def gptq_quantize(W: torch.Tensor, U: torch.Tensor, q_type: int, block_size: int = 128, rmin: float = -1.0,
                   rdelta: float = 0.1, nstep: int = 20, mode: int = L.GQ_MODE_EXACT, packed: bool = True,
                   wdeq_dtype: Optional[torch.dtype] = None, search_flags: bool = False,
-                  stream: Optional["torch.cuda.Stream"] = None):
-    """The column loop of one layer (gptq.py:146-295).  W: fp32 working copy, CLOBBERED.
-    Returns (qweight, d, sq, dmin, zq, packed|None, wdeq|None, flags|None).
+                  stream: Optional["torch.cuda.Stream"] = None, static_groups: bool = False,
+                  perm: Optional[torch.Tensor] = None):
+    """The column loop of one layer (gptq.py:146-295).  W: fp32 working copy in the ORIGINAL column order, CLOBBERED.
+    Returns (qweight, d, sq, dmin, zq, packed|None, wdeq|None, flags|None), all in the original column order.
     stream: enqueue on this side stream (outputs are allocated on the CURRENT stream, which the side stream first
-    waits for; the caller waits on the side stream before consuming the results)."""
+    waits for; the caller waits on the side stream before consuming the results).
+    static_groups (gptq.py:184-196): scales searched up front on W.  perm (act_order, gptq.py:209-216, needs
+    static_groups): permutation of the columns, U must belong to H[perm][:, perm].  Q3_K ignores both (:204-206)."""
     L.require_cuda(W, U)
     assert W.dtype == torch.float32 and W.is_contiguous() and U.dtype == torch.float32 and U.is_contiguous()
     d_row, d_col = W.shape
-    qweight, d, sq, dmin, zq, pk, wd = alloc_outputs(q_type, d_row, d_col, W.device, packed, wdeq_dtype)
+    if int(q_type) == 11:
+        static_groups, perm = False, None
+    assert perm is None or static_groups, "act_order requires static_groups (gptq.py:45-46)"
+    fused = perm is None
+    qweight, d, sq, dmin, zq, pk, wd = alloc_outputs(q_type, d_row, d_col, W.device, packed and fused,
+                                                     wdeq_dtype if fused else None)
     flags = torch.zeros(d_col // QK_K, 2, dtype=torch.int32, device=W.device) if search_flags else None
     lib = L.load()
     nws = lib.gq_gptq_workspace_bytes(d_row, d_col, int(mode))
@@ -155,10 +163,26 @@ def gptq_quantize(W: torch.Tensor, U: torch.Tensor, q_type: int, block_size: int
         stream.wait_stream(torch.cuda.current_stream(W.device))
     with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
         with _span("gptq"):
-            L.check(lib.gq_gptq_quantize(
-                L.ptr(W), L.ptr(U), d_row, d_col, int(q_type), int(block_size), float(rmin), float(rdelta), int(nstep), int(mode),
-                L.ptr(qweight), L.ptr(d), L.ptr(sq), L.ptr(dmin), L.ptr(zq), L.ptr(pk), L.ptr(wd),
-                L.dtype_code(wdeq_dtype) if wdeq_dtype is not None else 0, L.ptr(flags), L.ptr(ws), nws, L.stream_of(W.device)))
+            sg, Wk, pm, qk = (1 if static_groups else 0), W, None, qweight
+            if perm is not None:
+                # scales on the un-permuted weights (= the RTN search, quantizer.py:285-300 does the same loop), then the
+                # loop on W[:, perm]; the codes come back in loop order
+                scratch = torch.empty_like(qweight)
+                L.check(lib.gq_rtn_quantize(L.ptr(W), L.GQ_F32, d_row, d_col, int(q_type), float(rmin), float(rdelta), int(nstep),
+                                            L.ptr(scratch), L.ptr(d), L.ptr(sq), L.ptr(dmin), L.ptr(zq), None, None, 0,
+                                            L.stream_of(W.device)))
+                pm = perm.to(torch.int32).contiguous()
+                Wk = W.index_select(1, perm).contiguous()
+                sg, qk = 2, scratch
+            L.check(lib.gq_gptq_quantize_ex(
+                L.ptr(Wk), L.ptr(U), d_row, d_col, int(q_type), int(block_size), float(rmin), float(rdelta), int(nstep), int(mode),
+                sg, L.ptr(pm), L.ptr(qk), L.ptr(d), L.ptr(sq), L.ptr(dmin), L.ptr(zq), L.ptr(pk), L.ptr(wd),
+                L.dtype_code(wdeq_dtype) if (wdeq_dtype is not None and fused) else 0, L.ptr(flags), L.ptr(ws), nws,
+                L.stream_of(W.device)))
+            if perm is not None:
+                qweight.index_copy_(1, perm, qk)                    # gptq.py:276-277: qweight[:, invperm]
+                pk = pack(q_type, qweight, d, sq, dmin, zq) if packed else None
+                wd = dequantize(q_type, qweight, d, sq, dmin, zq, wdeq_dtype) if wdeq_dtype is not None else None
     return qweight, d, sq, dmin, zq, pk, wd, flags
 
 

@@ -295,12 +295,25 @@ class Quantizer:
                     masks = torch.stack([(w == 0).all(dim=0) for w in W.split(rows, dim=0)])
                     self._mask_flags.append((names, (masks != masks[0:1]).any()))   # checked at the end (no host sync here)
                 side = self._side_stream(gi) if overlap else None
-                U, not_pd = ops.prepare(acc.H, W, kw.get("rel_damp", 1e-2), stream=side, slot=1 + gi if overlap else 0)  # gptq.py:305-324
+                # act_order (gptq.py:209-216): the loop runs on W[:, perm] with the factor of H[perm][:, perm]; Q3_K
+                # members ignore it (gptq.py:204-206) and need the plain factor
+                q3 = [quant_config.get(n.split(".")[-1], GGMLQuantizationType.Q4_K) == GGMLQuantizationType.Q3_K for n in names]
+                perm = U_perm = U = None
+                not_pd = []          # device flags (one per factorisation), read only at the end
+                if kw.get("act_order", False) and not all(q3):
+                    perm = torch.argsort(torch.diag(acc.H), descending=True)
+                    Hp = acc.H.index_select(0, perm).index_select(1, perm).contiguous()
+                    U_perm, flag = ops.prepare(Hp, W.index_select(1, perm).contiguous(), kw.get("rel_damp", 1e-2),
+                                               stream=side, slot=1 + gi if overlap else 0)
+                    not_pd.append(flag)
+                if perm is None or any(q3):
+                    U, flag = ops.prepare(acc.H, W, kw.get("rel_damp", 1e-2), stream=side, slot=1 + gi if overlap else 0)  # gptq.py:305-324
+                    not_pd.append(flag)
                 done = None
                 if side is not None:
                     done = torch.cuda.Event()
                     done.record(side)
-            plans.append((names, hs, rows, W, U, not_pd, done, side))
+            plans.append((names, hs, rows, W, U, not_pd, done, side, perm, U_perm))
         deferred = None
         if defer is not None:
             hit = [pl for pl in plans if pl[0] == [defer]]
@@ -340,10 +353,16 @@ class Quantizer:
         for r in rows:
             offs.append(offs[-1] + r)
         launched = []
+        perm, U_perm = plan[8], plan[9]
+        static = bool(self.quantizer_kwargs.get("static_groups", False))
         for qt, idxs in by_type.items():
             self._log(f"Quantizing {[names[i] for i in idxs]} with {GGMLQuantizationType(qt).name}.")
             Wg = W if len(idxs) == len(hs) else torch.cat([W[offs[i]:offs[i + 1]] for i in idxs], 0).contiguous()
-            launched.append((qt, idxs, self._sharded_gptq(Wg, U, qt, dtype, rank, world, stream)))
+            if qt == int(GGMLQuantizationType.Q3_K) or perm is None:
+                outs = self._sharded_gptq(Wg, U, qt, dtype, rank, world, stream, static and qt != int(GGMLQuantizationType.Q3_K), None)
+            else:
+                outs = self._sharded_gptq(Wg, U_perm, qt, dtype, rank, world, stream, True, perm)
+            launched.append((qt, idxs, outs))
         return launched
 
     def _finish_group(self, plan, launched):
@@ -372,11 +391,11 @@ class Quantizer:
             self._side_streams.append(torch.cuda.Stream(priority=hi))
         return self._side_streams[i]
 
-    def _sharded_gptq(self, W, U, qt, dtype, rank, world, stream=None):
+    def _sharded_gptq(self, W, U, qt, dtype, rank, world, stream=None, static_groups=False, perm=None):
         kw = self.quantizer_kwargs
         args = dict(block_size=kw.get("block_size", 128) or W.shape[1], rmin=kw.get("rmin", -1.0),
                     rdelta=kw.get("rdelta", 0.1), nstep=kw.get("nstep", 20), packed=True, wdeq_dtype=dtype,
-                    mode={"exact": 0, "fast": 1}[kw.get("mode", "exact")])
+                    mode={"exact": 0, "fast": 1}[kw.get("mode", "exact")], static_groups=static_groups, perm=perm)
         if world == 1:
             return ops.gptq_quantize(W, U, qt, stream=stream, **args)[:7]
         total = W.shape[0]
@@ -609,7 +628,7 @@ class Quantizer:
     def non_invertible_modules(self) -> List[str]:
         """Modules whose Hessian was not positive definite (U fell back to identity, gptq.py:321-323). Synchronises."""
         out = []
-        for names, flag in self._not_pd_flags:
-            if bool(flag.item()):
+        for names, flags in self._not_pd_flags:
+            if any(bool(f.item()) for f in flags):
                 out.extend(names)
         return out

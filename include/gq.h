@@ -94,7 +94,7 @@ GQ_API int gq_prepare(float *H, const float *W, int d_row, int d_col, float rel_
                void *workspace, size_t ws_bytes, int *not_pd_flag, gq_stream_t stream);
 
 /* The column-blocked quantise -> error -> rank-k-update loop -- replaces GPTQ.step (gptq.py:146-295)
- * for act_order = static_groups = False, one launch per layer.
+ * for act_order = static_groups = False (see gq_gptq_quantize_ex for those), one launch per layer.
  *   W     (d_row, d_col) fp32 working copy; CLOBBERED (holds the propagated errors on return).
  *   U     from gq_prepare.
  *   rmin, rdelta, nstep: K-quant search parameters (quant_utils.py:66-68), doubles like Python floats.
@@ -116,6 +116,22 @@ GQ_API int gq_gptq_quantize(float *W, const float *U, int d_row, int d_col, int 
                      void *qweight, uint16_t *d, void *sq, uint16_t *dmin, void *zq,
                      uint8_t *packed, void *wdeq, int wdeq_dtype, uint32_t *search_flags,
                      void *workspace, size_t ws_bytes, gq_stream_t stream);
+
+/* gq_gptq_quantize with the reference's two optional variants of GPTQ.step (gptq.py:184-216, 233-238, 273-277;
+ * GQ_MODE_EXACT only; Q3_K ignores both, gptq.py:204-206):
+ *   static_groups = 0  scales searched per super-block on the live weights (gq_gptq_quantize);
+ *                 = 1  all scales / zeros searched up front on W as passed (gptq.py:184-196);
+ *                 = 2  d, dmin, sq, zq already hold them on entry (the caller ran gq_get_scale_and_zero on the 256-column
+ *                      slabs of the UN-permuted weights -- needed for act_order, where W below is permuted).
+ *   perm (device int32[d_col], may be NULL) = act_order: W and U are in PERMUTED column order (W[:, perm], U from
+ *        H[perm][:, perm], perm = argsort(diag H, descending)); loop column c is original column perm[c] and uses that
+ *        column's group scales.  Requires static_groups = 2.  qweight comes out in LOOP order (the caller un-permutes it:
+ *        out[:, perm[c]] = qweight[:, c]); packed and wdeq must be NULL (use gq_pack / gq_dequantize afterwards). */
+GQ_API int gq_gptq_quantize_ex(float *W, const float *U, int d_row, int d_col, int qtype, int block_size,
+                        double rmin, double rdelta, int nstep, int mode, int static_groups, const int *perm,
+                        void *qweight, uint16_t *d, void *sq, uint16_t *dmin, void *zq,
+                        uint8_t *packed, void *wdeq, int wdeq_dtype, uint32_t *search_flags,
+                        void *workspace, size_t ws_bytes, gq_stream_t stream);
 
 /* Kernel-level timing of gq_gptq_quantize for benchmarks: when enabled, CUDA events are recorded around every launch of
  * the fused search / column-loop kernel (kind 0) and of the tcgen05 rank-k GEMM of GQ_MODE_FAST (kind 1).

@@ -269,20 +269,29 @@ static inline float q_dequant(float q, float d, float sq, float dm, float zq) {
 static inline float code_to_f(uint8_t b, int is_signed) { return is_signed ? (float)(int8_t)b : (float)b; }
 
 /* ------------------------------------------------------------------------------------------
- * GPTQ.step: gptq.py:146-295 (act_order = static_groups = False).
- * W (d_row, d_col) fp32 row-major, IN: weights after quantization_pre_step; OUT: the
- * dequantised weights (gptq.py:266 writes w_q back into w).
- * U = H_inv_cho, upper triangular, element (i,j) at U[i*u_rs + j*u_cs].
+ * GPTQ.step: gptq.py:146-295.
+ * W (d_row, d_col) fp32 row-major, IN: weights after quantization_pre_step (ORIGINAL column order);
+ * OUT: the dequantised weights in the original column order (gptq.py:266 writes w_q back into w; with
+ * act_order w lives in permuted order and dequantize_linear_weight of the un-permuted codes is what the
+ * caller writes back, quantizer.py:257-264 -- the same values).
+ * U = H_inv_cho, upper triangular, element (i,j) at U[i*u_rs + j*u_cs]; with act_order it belongs to the
+ * PERMUTED Hessian H[perm][:, perm] (gptq.py:212-213).
+ * static_groups (gptq.py:184-196): all scales / zeros are searched up front on the original W.
+ * perm (act_order, gptq.py:209-216; requires static_groups, :45-46): column c of the loop is original
+ * column perm[c]; its group / super-group are perm[c]/group_size, perm[c]/256 (:233-235); the codes are
+ * un-permuted at the end (:276-277).  NULL = no act_order.
+ * Q3_K ignores both options (gptq.py:204-206) -- the caller passes 0 / NULL for it.
  * Outputs: qweight (d_row,d_col) codes (uint8 / int8 bit patterns); d,dmin (d_row, d_col/256) fp16
  * bits; sq,zq (d_row, d_col/group_size).
  * ---------------------------------------------------------------------------------------- */
-int orc_gptq_step(float *W, const float *U, long u_rs, long u_cs, int d_row, int d_col, int qtype,
-                  int block_size, double rmin, double rdelta, int nstep,
-                  uint8_t *qweight, uint16_t *d, uint16_t *dmin, uint8_t *sq, uint8_t *zq,
-                  uint32_t *flags /* 2 per super-block or NULL */) {
+int orc_gptq_step_ex(float *W, const float *U, long u_rs, long u_cs, int d_row, int d_col, int qtype,
+                     int block_size, double rmin, double rdelta, int nstep, int static_groups, const int *perm,
+                     uint8_t *qweight, uint16_t *d, uint16_t *dmin, uint8_t *sq, uint8_t *zq,
+                     uint32_t *flags /* 2 per super-block or NULL */) {
     orc_fmt_t f;
     if (orc_fmt(qtype, &f)) return -1;
     if (d_col % QK_K) return -2;
+    if (perm && !static_groups) return -3;
     const int n = f.group_size, ng = d_col / n, nsb = d_col / QK_K, gpr = QK_K / n;
     const int is_signed = !f.asym;
     const float lo = (float)f.qmin, hi = (float)f.qmax;
@@ -292,21 +301,39 @@ int orc_gptq_step(float *W, const float *U, long u_rs, long u_cs, int d_row, int
         for (long j = 0; j < d_col; ++j) Ur[i * d_col + j] = U[i * u_rs + j * u_cs];
     float *errs = (float *)malloc(sizeof(float) * (size_t)d_row * block_size);
 
+    if (static_groups) {                                            /* gptq.py:184-196, on the original w */
+        for (int s = 0; s < nsb; ++s)
+            orc_get_scale_and_zero(W + (long)s * QK_K, d_col, d_row, qtype, rmin, rdelta, nstep,
+                                   d + s, nsb, dmin + s, nsb, sq + (long)s * gpr, ng, zq + (long)s * gpr, ng,
+                                   flags ? flags + 2 * s : NULL);
+    }
+    if (perm) {                                                     /* gptq.py:211: w = w[:, perm] */
+        float *tmp = (float *)malloc(sizeof(float) * d_col);
+        for (int r = 0; r < d_row; ++r) {
+            float *wrow = W + (long)r * d_col;
+            for (int c = 0; c < d_col; ++c) tmp[c] = wrow[perm[c]];
+            memcpy(wrow, tmp, sizeof(float) * d_col);
+        }
+        free(tmp);
+    }
+    uint8_t *qw = perm ? (uint8_t *)malloc((size_t)d_row * d_col) : qweight;
+
     for (int c1 = 0; c1 < d_col; c1 += block_size) {               /* gptq.py:222 */
         const int c2 = c1 + block_size < d_col ? c1 + block_size : d_col;
         const int ncols = c2 - c1;
         /* Super-block searches that start inside this block read the LIVE matrix w
          * (gptq.py:240-241), i.e. without this block's rank-1 updates (those only touch w_blk). */
-        for (int i = 0; i < ncols; ++i) {
-            const int col = c1 + i;
-            if (col % QK_K == 0) {
-                const int s = col / QK_K;
-                orc_get_scale_and_zero(W + col, d_col, d_row, qtype, rmin, rdelta, nstep,
-                                       d + s, nsb, dmin + s, nsb,
-                                       sq + (long)s * gpr, ng, zq + (long)s * gpr, ng,
-                                       flags ? flags + 2 * s : NULL);
+        if (!static_groups)
+            for (int i = 0; i < ncols; ++i) {
+                const int col = c1 + i;
+                if (col % QK_K == 0) {
+                    const int s = col / QK_K;
+                    orc_get_scale_and_zero(W + col, d_col, d_row, qtype, rmin, rdelta, nstep,
+                                           d + s, nsb, dmin + s, nsb,
+                                           sq + (long)s * gpr, ng, zq + (long)s * gpr, ng,
+                                           flags ? flags + 2 * s : NULL);
+                }
             }
-        }
 #pragma omp parallel for schedule(static)
         for (int r = 0; r < d_row; ++r) {
             float wb[1024];
@@ -314,7 +341,9 @@ int orc_gptq_step(float *W, const float *U, long u_rs, long u_cs, int d_row, int
             float *er = errs + (long)r * block_size;
             memcpy(wb, wrow + c1, sizeof(float) * ncols);            /* gptq.py:225 */
             for (int i = 0; i < ncols; ++i) {
-                const int col = c1 + i, s = col / QK_K, g = col / n;
+                const int col = c1 + i;
+                const int ocol = perm ? perm[col] : col;             /* :233-238 group of the ORIGINAL column */
+                const int s = ocol / QK_K, g = ocol / n;
                 const float *urow = Ur + (long)col * d_col + c1;     /* U[col, c1:c2] */
                 const float dd = h2f(d[(long)r * nsb + s]), dm = h2f(dmin[(long)r * nsb + s]);
                 const float fs = code_to_f(sq[(long)r * ng + g], is_signed);
@@ -322,7 +351,7 @@ int orc_gptq_step(float *W, const float *U, long u_rs, long u_cs, int d_row, int
                 const float x = wb[i];
                 const float q = q_quant(x, dd, fs, dm, fz, lo, hi);  /* :247-254 */
                 const float wq = q_dequant(q, dd, fs, dm, fz);       /* :255-261 */
-                qweight[(long)r * d_col + col] = (uint8_t)(int8_t)(int)q; /* :263 */
+                qw[(long)r * d_col + col] = (uint8_t)(int8_t)(int)q; /* :263 */
                 const float err = (x - wq) / urow[i];                /* :264 */
                 wrow[col] = wq;                                      /* :266 */
                 const float nerr = -err;                             /* alpha=-1 folded into vec1 */
@@ -348,8 +377,27 @@ int orc_gptq_step(float *W, const float *U, long u_rs, long u_cs, int d_row, int
             }
         }
     }
+    if (perm) {                                                     /* gptq.py:276-277: qweight[:, invperm]; same for w */
+        float *tmp = (float *)malloc(sizeof(float) * d_col);
+        for (int r = 0; r < d_row; ++r) {
+            float *wrow = W + (long)r * d_col;
+            for (int c = 0; c < d_col; ++c) {
+                qweight[(long)r * d_col + perm[c]] = qw[(long)r * d_col + c];
+                tmp[perm[c]] = wrow[c];
+            }
+            memcpy(wrow, tmp, sizeof(float) * d_col);
+        }
+        free(tmp); free(qw);
+    }
     free(errs); free(Ur);
     return 0;
+}
+
+int orc_gptq_step(float *W, const float *U, long u_rs, long u_cs, int d_row, int d_col, int qtype,
+                  int block_size, double rmin, double rdelta, int nstep,
+                  uint8_t *qweight, uint16_t *d, uint16_t *dmin, uint8_t *sq, uint8_t *zq, uint32_t *flags) {
+    return orc_gptq_step_ex(W, U, u_rs, u_cs, d_row, d_col, qtype, block_size, rmin, rdelta, nstep, 0, NULL,
+                            qweight, d, dmin, sq, zq, flags);
 }
 
 /* ------------------------------------------------------------------------------------------

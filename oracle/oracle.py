@@ -82,9 +82,10 @@ def get_scale_and_zero(x: np.ndarray, qtype: int, rmin=-1.0, rdelta=0.1, nstep=2
 
 
 def gptq_step(W: np.ndarray, U: np.ndarray, qtype: int, block_size=128, rmin=-1.0, rdelta=0.1, nstep=20,
-              return_flags=False):
+              return_flags=False, static_groups=False, perm=None):
     """gptq.py:146-295.  W (d_row,d_col) fp32 (not modified), U upper-triangular (any strides).
-    Returns (qweight, d, sq, dmin, zq, w_dequant)."""
+    static_groups / perm (act_order: perm = argsort(diag H, descending), U from the permuted H): gptq.py:184-216.
+    Returns (qweight, d, sq, dmin, zq, w_dequant), all in the original column order."""
     Wc = np.array(W, dtype=np.float32, order="C", copy=True)
     U = np.asarray(U, dtype=np.float32)
     d_row, d_col = Wc.shape
@@ -97,10 +98,14 @@ def gptq_step(W: np.ndarray, U: np.ndarray, qtype: int, block_size=128, rmin=-1.
     zq = np.empty((d_row, ng), np.uint8)
     flags = np.zeros((nsb, 2), np.uint32)
     rs, cs = U.strides[0] // 4, U.strides[1] // 4
-    rc = lib().orc_gptq_step(
+    if qtype == 11:                      # Q3_K: both options are forced off (gptq.py:204-206)
+        static_groups, perm = False, None
+    pm = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+    rc = lib().orc_gptq_step_ex(
         _p(Wc, C.c_float), _p(U, C.c_float), C.c_long(rs), C.c_long(cs),
         C.c_int(d_row), C.c_int(d_col), C.c_int(qtype), C.c_int(block_size),
-        C.c_double(rmin), C.c_double(rdelta), C.c_int(nstep),
+        C.c_double(rmin), C.c_double(rdelta), C.c_int(nstep), C.c_int(1 if static_groups else 0),
+        _p(pm, C.c_int) if pm is not None else None,
         _p(qw, C.c_uint8), _p(d, C.c_uint16), _p(dmin, C.c_uint16), _p(sq, C.c_uint8), _p(zq, C.c_uint8),
         _p(flags, C.c_uint32))
     assert rc == 0, rc

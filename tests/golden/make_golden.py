@@ -112,6 +112,54 @@ def b1_case(name, d_row, d_col, seed, n_seq=6, seq_len=96, block_size=128, wscal
     return out
 
 
+def variants_case(name, d_row, d_col, seed, n_seq=6, seq_len=96):
+    """static_groups and act_order (+ static_groups) variants of GPTQ.step (gptq.py:184-216, 233-238, 273-277).
+    Stored per (variant, type): the permutation the reference derived from diag(H) (act_order), the U it factored
+    from the permuted Hessian, and its five outputs (IEEE-sqrt reference only)."""
+    gen = torch.Generator().manual_seed(seed)
+    W = torch.randn(d_row, d_col, generator=gen) * 0.05
+    W = W * torch.exp(0.5 * torch.randn(d_row, 1, generator=gen))
+    xs = correlated_x(gen, n_seq, seq_len, d_col)
+    out = {"W": W.numpy()}
+    for vname, kw in (("static", dict(static_groups=True)), ("actorder", dict(static_groups=True, act_order=True))):
+        for q_type in TYPES:
+            set_sqrt(True)
+            layer = torch.nn.Linear(d_col, d_row, bias=False)
+            layer.weight.data = W.clone()
+            h = GPTQ(layer, rel_damp=0.01, block_size=128, **kw)
+            for x in xs:
+                h.update(x)
+            keep = {}
+            orig = h._prepare
+
+            def prep():
+                # called after the act_order permutation of W / H (gptq.py:209-216): record what the loop will see
+                keep["H_diag_order"] = torch.argsort(torch.diag(h.H), descending=True)
+                return keep.setdefault("U", orig())
+            h._prepare = prep
+            H0 = None
+
+            def pre_step_hook(orig_pre=h.quantization_pre_step):
+                orig_pre()
+                keep["H0"] = h.H.clone()
+            h.quantization_pre_step = pre_step_hook
+            five = [t.clone() for t in h.quantize(q_type)]
+            set_sqrt(False)
+            U = keep["U"]
+            uses_perm = vname == "actorder" and q_type != T.Q3_K            # Q3_K forces both options off (gptq.py:204-206)
+            # U and perm are the same for every type of a kind: stored once ("U_plain", "U_perm" + "perm")
+            if uses_perm:
+                perm = torch.argsort(torch.diag(keep["H0"]), descending=True).numpy().astype(np.int32)
+                assert np.array_equal(out.setdefault("perm", perm), perm)
+                assert np.array_equal(out.setdefault("U_perm", U.contiguous().numpy()), U.contiguous().numpy())
+            else:
+                assert np.array_equal(out.setdefault("U_plain", U.contiguous().numpy()), U.contiguous().numpy())
+            for k, v in np5(five).items():
+                out[f"{vname}_{q_type.name}_{k}"] = v
+    np.savez_compressed(os.path.join(HERE, f"variants_{name}.npz"), **out)
+    return out
+
+
 def search_case():
     """Edge cases for get_scale_and_zero (quant_utils.py:90-145)."""
     gen = torch.Generator().manual_seed(7)
@@ -202,6 +250,7 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     b1_case("a", d_row=48, d_col=512, seed=0)
     b1_case("b", d_row=20, d_col=768, seed=1, dead_col=5)
+    variants_case("a", d_row=24, d_col=512, seed=5)
     search_case()
     rtn_case()
     stats = {"torch": torch.__version__, "threads": torch.get_num_threads(),

@@ -125,7 +125,7 @@ def _tiny_model(seed=0):
     return LlamaForCausalLM(cfg).float().eval()
 
 
-def _run_driver(monkeypatch, tmp_path, tag, quant_config=None, **kw):
+def _run_driver(monkeypatch, tmp_path, tag, quant_config=None, quantizer_kwargs_extra=None, **kw):
     from tests import _oracle_backend as ob
     ob.install(monkeypatch)
     from gptq_gguf_toolkit_b200.quant import build_quant_config
@@ -135,8 +135,9 @@ def _run_driver(monkeypatch, tmp_path, tag, quant_config=None, **kw):
     loader = [([], {"input_ids": torch.randint(0, 512, (1, 64), generator=g)}) for _ in range(4)]
     save_dir = str(tmp_path / tag)
     q = Quantizer(model, data_loader=loader, quantizable_modules=r".*layers.*((q|k|v|o|gate|up|down)_proj)$",
-                  quantizer_kwargs=dict(rel_damp=0.01, block_size=128, act_order=False, quant_scale="absmax",
-                                        static_groups=False, rmin=-1.0, rdelta=0.1, nstep=20, verbose=False),
+                  quantizer_kwargs={**dict(rel_damp=0.01, block_size=128, act_order=False, quant_scale="absmax",
+                                           static_groups=False, rmin=-1.0, rdelta=0.1, nstep=20, verbose=False),
+                                    **(quantizer_kwargs_extra or {})},
                   pre_block_modules=["model.embed_tokens"], block_modules="model.layers", post_block_modules=["lm_head"],
                   quant_non_block_modules=True, device="cpu", save_dir=save_dir, keep_results=True, **kw)
     q.quantize(quant_config or build_quant_config("Q4_K", None))
@@ -205,8 +206,8 @@ def test_gptq_handle_protocol(monkeypatch):
     assert len(out) == 5 and out[0].shape == (16, 256) and h.packed.shape == (16, 144) and h.wdeq.dtype == layer.weight.dtype
     h.reset()
     assert h.H is None and h.num_samples == 0
-    with pytest.raises(NotImplementedError):
-        GPTQ(layer, act_order=True, static_groups=True)
+    with pytest.raises(AssertionError):
+        GPTQ(layer, act_order=True, static_groups=False)        # gptq.py:45-46
     acc = HessianAccumulator(256)
     a, b = GPTQ(layer, block_size=128, hessian=acc), GPTQ(torch.nn.Linear(256, 8, bias=False), block_size=128, hessian=acc)
     a.update(torch.randn(1, 40, 256))
@@ -215,6 +216,47 @@ def test_gptq_handle_protocol(monkeypatch):
     assert acc.H is not None            # still owned by b
     b.quantize(12); b.reset()
     assert acc.H is None
+
+
+def test_act_order_and_static_groups_host_logic(monkeypatch, tmp_path):
+    """GPTQ handle + driver with act_order / static_groups (gptq.py:184-216): permutation from diag(H), factor of the
+    permuted Hessian, Q3_K exemption (:204-206); handle and driver must agree with a direct oracle call."""
+    from tests import _oracle_backend as ob
+    ob.install(monkeypatch)
+    from gptq_gguf_toolkit_b200.gptq import GPTQ
+    torch.manual_seed(0)
+    layer = torch.nn.Linear(256, 16, bias=False)
+    W0 = layer.weight.data.clone()
+    xs = [torch.randn(2, 40, 256) * torch.linspace(0.2, 3.0, 256) for _ in range(3)]
+    for qt in (12, 11):
+        layer.weight.data = W0.clone()
+        h = GPTQ(layer, rel_damp=0.01, block_size=128, act_order=True, static_groups=True)
+        for x in xs:
+            h.update(x)
+        H = h.H.clone()
+        five = h.quantize(qt)
+        perm = None if qt == 11 else torch.argsort(torch.diag(H), descending=True)
+        Hp = H if perm is None else H[perm][:, perm]
+        Wp = W0 if perm is None else W0[:, perm]
+        U = orc.prepare(Hp.numpy().copy(), Wp.numpy().copy(), 0.01)[0]
+        ref = orc.gptq_step(W0.numpy(), U, qt, static_groups=True, perm=None if perm is None else perm.numpy())
+        for got, want in zip(five, ref[:5]):
+            assert np.array_equal(got.numpy().view(np.uint8), np.ascontiguousarray(want).view(np.uint8))
+        if qt == 12:
+            assert not torch.equal(perm, torch.arange(256))      # the test really permutes
+    # driver: act_order changes the result, keeps the schema, and the written weights are the dequantised codes
+    kw = dict(quantizer_kwargs_extra=dict(act_order=True, static_groups=True))
+    model_a, qa, _ = _run_driver(monkeypatch, tmp_path, "ao", **kw)
+    model_b, qb, _ = _run_driver(monkeypatch, tmp_path, "plain")
+    name = "model.layers.0.mlp.down_proj"
+    assert not torch.equal(qa.results[name]["qweight"], qb.results[name]["qweight"])
+    d = qa.results[name]
+    deq = orc.dequantize(12, d["qweight"].numpy(), d["super_group_scale"].numpy(), d["group_scale_quant"].numpy(),
+                         d["super_group_zero"].numpy(), d["group_zero_quant"].numpy())
+    assert np.array_equal(deq, model_a.get_submodule(name).weight.data.numpy())
+    assert np.array_equal(d["packed"].numpy(), orc.pack(12, d["qweight"].numpy(), d["super_group_scale"].numpy(),
+                                                        d["group_scale_quant"].numpy(), d["super_group_zero"].numpy(),
+                                                        d["group_zero_quant"].numpy()))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -111,3 +111,21 @@ def test_prepare_factorisation_properties():
     assert np.allclose(U.T.astype(np.float64) @ U.astype(np.float64), inv, rtol=1e-3, atol=1e-6)
 
     assert np.all(Hd[3, :3] == 0) and np.all(Hd[:3, 3] == 0)
+
+
+@pytest.mark.parametrize("variant", ["static", "actorder"])
+@pytest.mark.parametrize("tname", list(TYPES))
+def test_static_groups_and_act_order_match_reference(golden_dir, variant, tname):
+    """gptq.py:184-216, 233-238, 273-277: scales searched up front on the original W (static_groups), columns visited
+    in descending diag(H) order with per-column group lookup (act_order); Q3_K ignores both (:204-206)."""
+    g = _load(golden_dir, "variants_a.npz")
+    uses_perm = variant == "actorder" and tname != "Q3_K"
+    o = orc.gptq_step(g["W"], g["U_perm"] if uses_perm else g["U_plain"], TYPES[tname], static_groups=True,
+                      perm=g["perm"] if uses_perm else None)
+    got = _five_raw(o)
+    for k in KEYS:
+        ref = g[f"{variant}_{tname}_{k}"]
+        assert np.array_equal(got[k].view(ref.dtype), ref), f"{variant} {tname} {k}"
+    # the weights handed back are the dequantisation of those outputs, in the original column order
+    five = [got["qweight"].view(o[0].dtype), o[1], o[2], o[3], o[4]]
+    assert np.array_equal(o[5], orc.dequantize(TYPES[tname], *five))
