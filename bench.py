@@ -238,6 +238,7 @@ def main():
                     help="side-stream Cholesky chains: overlap the column loops too (eager) or run before them (staged)")
     ap.add_argument("--no-early-exit", action="store_true", help="ablation: run the full block in forward pass 1")
     ap.add_argument("--no-defer", action="store_true", help="ablation: no split of forward pass 2 at the last quantised layer")
+    ap.add_argument("--no-fused-forward", action="store_true", help="ablation: HF's eager RMSNorm / rotary / SiLU*up kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -289,7 +290,8 @@ def main():
                       pre_block_modules=["model.embed_tokens"], block_modules="model.layers", post_block_modules=["lm_head"],
                       quant_non_block_modules=True, device=device, save_dir=None, keep_results=e2e,
                       calibration_batch_size=args.batch, timer=timer, overlap_prepare=False if args.no_overlap else args.overlap,
-                      early_exit_pass1=not args.no_early_exit, defer_last_layer=not args.no_defer)
+                      early_exit_pass1=not args.no_early_exit, defer_last_layer=not args.no_defer,
+                      fused_forward_ops=not args.no_fused_forward)
         if not e2e:
             restore_from_hbm()
         torch.cuda.synchronize()

@@ -16,6 +16,7 @@ What is different (B200-first, results unchanged):
 """
 from __future__ import annotations
 
+import contextlib
 import os
 import threading
 import queue
@@ -118,7 +119,7 @@ class Quantizer:
                  # ---- additions over the reference ----
                  calibration_batch_size: int = 8, share_hessians: bool = True, keep_results: bool = False,
                  save_packed: bool = True, timer: Optional[PhaseTimer] = None, early_exit_pass1: bool = True,
-                 overlap_prepare: bool = True, defer_last_layer: bool = True) -> None:
+                 overlap_prepare: bool = True, defer_last_layer: bool = True, fused_forward_ops: bool = True) -> None:
         self.model = model
         self.data_loader = data_loader
         self.quantizable_modules = quantizable_modules
@@ -139,6 +140,8 @@ class Quantizer:
         self.early_exit_pass1 = early_exit_pass1
         self.overlap_prepare = overlap_prepare
         self.defer_last_layer = defer_last_layer
+        self.fused_forward_ops = fused_forward_ops
+        self.fused_installed: List[str] = []
         self._split_ok: Optional[bool] = None
         self._side_streams: list = []
         self._mask_flags: list = []
@@ -507,6 +510,16 @@ class Quantizer:
     # -------------------------------------------------------------------------------------------
     @torch.no_grad()
     def quantize(self, quant_config: Dict[str, GGMLQuantizationType]) -> None:
+        """quantizer.py:59-217.  With `fused_forward_ops` the element-wise pieces of HF's block forward (RMSNorm, rotary
+        embedding, SiLU*up) are swapped for single-pass kernels for the duration of the run (fused_forward.py: each
+        replacement is verified against the module it replaces when installed, everything is restored afterwards)."""
+        from .fused_forward import fused_forward
+        ctx = fused_forward(self.model, self.verbose) if self.fused_forward_ops else contextlib.nullcontext([])
+        with ctx as installed:
+            self.fused_installed = list(installed)
+            self._quantize_impl(quant_config)
+
+    def _quantize_impl(self, quant_config: Dict[str, GGMLQuantizationType]) -> None:
         device = self.device or next(self.model.parameters()).device
         self._not_pd_flags = []
         self._mask_flags = []
