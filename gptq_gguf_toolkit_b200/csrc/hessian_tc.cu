@@ -48,19 +48,33 @@ __device__ __forceinline__ void tile_coords(int idx, int ntn, int &tm, int &tn) 
 // ---------------------------------------------------------------------------------------------
 // X (T x n) -> Xt (n x Tp), zero padded in t
 // ---------------------------------------------------------------------------------------------
+// (64 tokens x 64 channels) tiles; 128-bit global loads and stores on both sides, the transposition itself moves
+// 32-bit words holding two consecutive tokens of one channel through a conflict-free (stride 33) shared-memory tile.
 __global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t *__restrict__ X, uint16_t *__restrict__ Xt,
                                                           int T, int n, int Tp) {
-    __shared__ uint16_t tile[64][66];
+    __shared__ uint32_t tile[64 * 33];
     const int t0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
-    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 x 4
+    {
+        const int tp = threadIdx.x >> 3, v = threadIdx.x & 7;          // token pair, group of 8 channels
+        const int ta = t0 + 2 * tp, tb = ta + 1;
+        union { uint4 u; uint16_t h[8]; } r0, r1;
+        r0.u = make_uint4(0, 0, 0, 0);
+        r1.u = make_uint4(0, 0, 0, 0);
+        if (ta < T) r0.u = *reinterpret_cast<const uint4 *>(X + (size_t)ta * n + c0 + 8 * v);
+        if (tb < T) r1.u = *reinterpret_cast<const uint4 *>(X + (size_t)tb * n + c0 + 8 * v);
 #pragma unroll
-    for (int r = ty; r < 64; r += 4) {
-        const int t = t0 + r;
-        tile[r][tx] = (t < T) ? X[(size_t)t * n + c0 + tx] : (uint16_t)0;
+        for (int e = 0; e < 8; ++e) tile[(8 * v + e) * 33 + tp] = (uint32_t)r0.h[e] | ((uint32_t)r1.h[e] << 16);
     }
     __syncthreads();
+    {
+        const int c = threadIdx.x >> 2, q = threadIdx.x & 3;           // channel, group of 16 tokens
+        uint32_t w[8];
 #pragma unroll
-    for (int r = ty; r < 64; r += 4) Xt[(size_t)(c0 + r) * Tp + t0 + tx] = tile[tx][r];
+        for (int j = 0; j < 8; ++j) w[j] = tile[c * 33 + 8 * q + j];
+        uint4 *dst = reinterpret_cast<uint4 *>(Xt + (size_t)(c0 + c) * Tp + t0 + 16 * q);
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
