@@ -369,7 +369,9 @@ def main():
             "kernel": "gptq_layer_kernel<Q4_K>: fused scale search + 128-step column loop + left-looking rank-k update + GGUF pack",
             "launches_per_step": n_layer_launch, "avg_launch_ms": 1e3 * t_gptq / max(1, n_layer_launch),
             "peak_source": pk["source"],
-            "note": ("exact mode: the rank-k update is an fp32 FFMA chain in the reference's order (bit-identical packed bytes), "
+            "note": ("launch durations are CUDA-event spans on the launching stream; the down_proj launches run on a side stream "
+                     "concurrently with the pass-2 block forwards, which lengthens them (alone: 21-30 TFLOP/s, profiles/). "
+                     "exact mode: the rank-k update is an fp32 FFMA chain in the reference's order (bit-identical packed bytes), "
                      "so it runs on the SIMT pipes (nominal 148 SMs x 128 FMA x 2 x clock ~ 72 TFLOP/s at 1.9 GHz), not on tensor "
                      "cores; the reference's right-looking form is HBM-bound at 32 flop/B (~209 TFLOP/s ceiling)"),
         }
