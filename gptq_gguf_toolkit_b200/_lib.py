@@ -12,7 +12,7 @@ SO_PATH = os.environ.get("GQ_LIB_PATH") or os.path.join(_HERE, "libgq.so")   # G
 
 GQ_OK, GQ_ERR_INVALID, GQ_ERR_CUDA, GQ_ERR_UNSUPPORTED, GQ_ERR_WORKSPACE = 0, 1, 2, 3, 4
 GQ_F32, GQ_F16, GQ_BF16 = 0, 1, 2
-GQ_MODE_EXACT, GQ_MODE_FAST = 0, 1
+GQ_MODE_EXACT, GQ_MODE_FAST, GQ_MODE_EXACT_LEFT, GQ_MODE_EXACT_RIGHT = 0, 1, 2, 3
 
 _DT = {torch.float32: GQ_F32, torch.float16: GQ_F16, torch.bfloat16: GQ_BF16}
 

@@ -16,6 +16,8 @@
 #include "f32x2.cuh"
 #include "gemm_tf32.cuh"
 #include "tile.cuh"
+#include <cmath>
+#include <cstdlib>
 
 namespace {
 
@@ -43,6 +45,10 @@ struct LayerParams {
     // GQ_MODE_FAST: the kernel handles super-blocks [sb_begin, sb_end) of an already updated W (the rank-k updates
     // between super-blocks run as tcgen05 GEMMs) and also emits the hi/lo TF32 split of its errors.
     int sb_begin, sb_end, fast;
+    // skip_bulk: the contributions of all EARLIER super-blocks have already been applied to W by separate launches
+    // (fast mode's tcgen05 GEMMs, or exact_update_kernel in the exact right-looking schedule); the kernel then only
+    // does the search, the column steps and the in-super-block update of [sb_begin, sb_end).
+    int skip_bulk;
     float *e_hi, *e_lo;     // (rows padded to 128) x 256, only in fast mode
     f2_t nz2;                  // {-0.0f, -0.0f}, deliberately a run-time value (see f2_mul_nofuse)
     // static_groups (gptq.py:184-196): d/dmin/sq/zq already hold the scales of EVERY super-block (searched on the
@@ -109,7 +115,8 @@ __device__ __forceinline__ int ud_idx(int i, int j) {
 // tile(8 rows x 4 cols per thread) -= E[:, kbeg:kend] * U[kbeg:kend, window]; the reference's addmm_ arithmetic.
 // HALF: only the window's columns 128..255 are updated (warps with ch == 1 compute, all warps load).
 template <bool HALF>
-__device__ __forceinline__ void rank_update(float (&w)[8][4], const LayerParams &p, Smem &sm, int r0, int c,
+__device__ __forceinline__ void rank_update(float (&w)[8][4], const LayerParams &p, float *__restrict__ Us_base,
+                                            float *__restrict__ Es_base, int r0, int c,
                                             int kbeg, int kend, int tid, int rg, int ch, int lane) {
     const int P = (kend - kbeg) / KP;
     const float *__restrict__ U = p.U;
@@ -118,8 +125,8 @@ __device__ __forceinline__ void rank_update(float (&w)[8][4], const LayerParams 
     auto issue = [&](int pc) {
         if (pc < P) {
             const int k0 = kbeg + KP * pc, st = pc % S;
-            float *us = sm.u.pipe.Us + st * US_FLOATS;
-            float *es = sm.u.pipe.Es + st * ES_FLOATS;
+            float *us = Us_base + st * US_FLOATS;
+            float *es = Es_base + st * ES_FLOATS;
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
                 const int id = tid + NT * m, row = id >> 6, c16 = id & 63;
@@ -145,8 +152,8 @@ __device__ __forceinline__ void rank_update(float (&w)[8][4], const LayerParams 
         __syncthreads();
         issue(pc + S - 1);
         if (!HALF || ch == 1) {
-            const float *us = sm.u.pipe.Us + (pc % S) * US_FLOATS + ch * 128 + 4 * lane;
-            const float *es = sm.u.pipe.Es + (pc % S) * ES_FLOATS + (8 * rg) * KP;
+            const float *us = Us_base + (pc % S) * US_FLOATS + ch * 128 + 4 * lane;
+            const float *es = Es_base + (pc % S) * ES_FLOATS + (8 * rg) * KP;
 #pragma unroll
             for (int kk = 0; kk < KP; kk += 4) {
                 float4 e[8];
@@ -344,7 +351,7 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
             w[i][0] = v.x; w[i][1] = v.y; w[i][2] = v.z; w[i][3] = v.w;
         }
         __syncthreads();   // previous super-block is completely done with the shared buffers
-        rank_update<false>(w, p, sm, r0, c, 0, p.fast ? 0 : c, tid, rg, ch, lane);   // fast mode: already applied by GEMMs
+        rank_update<false>(w, p, sm.u.pipe.Us, sm.u.pipe.Es, r0, c, 0, p.skip_bulk ? 0 : c, tid, rg, ch, lane);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
             *reinterpret_cast<float4 *>(sm.Wt + wt_idx4(8 * rg + i, ch * 32 + lane)) =
@@ -408,7 +415,7 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
                 w[i][0] = v.x; w[i][1] = v.y; w[i][2] = v.z; w[i][3] = v.w;
             }
         }
-        rank_update<true>(w, p, sm, r0, c, c, c + 128, tid, rg, ch, lane);
+        rank_update<true>(w, p, sm.u.pipe.Us, sm.u.pipe.Es, r0, c, c, c + 128, tid, rg, ch, lane);
         if (ch == 1) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -445,6 +452,82 @@ template <int QT> int launch_layer(const LayerParams &p, cudaStream_t st) {
     return GQ_OK;
 }
 
+// Exact right-looking schedule: the trailing update of ONE finished super-block (columns c .. c+255, whose propagated
+// errors E sit in W[:, c:c+256]) onto every later column, as a grid over (256-column windows) x (32-row groups):
+//     W[r, j] <- (W[r, j] - chain(E[r, c:c+128], U[c:c+128, j])) - chain(E[r, c+128:c+256], U[c+128:c+256, j])
+// -- per element the very same two roundings-per-128-k's sequence that the left-looking loop of gptq_layer_kernel applies
+// for these two blocks (rank_update<false> is shared), so the two schedules are bit-identical; what changes is who does
+// the work: with few row groups (a row slice of a projection on one of several GPUs, d_col = 14336) the left-looking
+// kernel leaves most SMs idle while each CTA walks its super-blocks alone, here every SM takes part in every update.
+__global__ void __launch_bounds__(NT, 2) exact_update_kernel(const LayerParams p, const int c) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    float *Us = reinterpret_cast<float *>(smem_raw);
+    float *Es = Us + S * US_FLOATS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rg = warp >> 1, ch = warp & 1;
+    const int r0 = blockIdx.y * R;
+    const int cw = c + GQ_QK_K * (1 + blockIdx.x);       // this CTA's window of 256 later columns
+    const size_t ld = (size_t)p.d_col;
+    float w[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int gr = min(r0 + 8 * rg + i, p.d_row - 1);
+        const float4 v = *reinterpret_cast<const float4 *>(p.W + (size_t)gr * ld + cw + ch * 128 + 4 * lane);
+        w[i][0] = v.x; w[i][1] = v.y; w[i][2] = v.z; w[i][3] = v.w;
+    }
+    rank_update<false>(w, p, Us, Es, r0, cw, c, c + GQ_QK_K, tid, rg, ch, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int gr = r0 + 8 * rg + i;
+        if (gr < p.d_row)
+            *reinterpret_cast<float4 *>(p.W + (size_t)gr * ld + cw + ch * 128 + 4 * lane) =
+                make_float4(w[i][0], w[i][1], w[i][2], w[i][3]);
+    }
+}
+
+int launch_exact_update(const LayerParams &p, int c, cudaStream_t st) {
+    const size_t smem = (size_t)S * (US_FLOATS + ES_FLOATS) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        GQ_CHECK_CUDA(cudaFuncSetAttribute(exact_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int nwin = (p.d_col - c - GQ_QK_K) / GQ_QK_K;
+    if (nwin <= 0) return GQ_OK;
+    dim3 grid(nwin, (p.d_row + R - 1) / R);
+    exact_update_kernel<<<grid, NT, smem, st>>>(p, c);
+    gq_count_launches(1);
+    GQ_CHECK_CUDA(cudaGetLastError());
+    return GQ_OK;
+}
+
+// Which exact schedule is faster?  A cost model in microseconds fitted to the measured kernel (profiles/r01_ncu_summary.md:
+// ~90 us of search + column steps per super-block and CTA wave, ~14.6 us of FFMA rank-k work per (32 x 256) window and
+// earlier super-block); the left-looking kernel pays the rank-k work serially inside each CTA, the right-looking schedule
+// spreads it over all SMs but launches twice per super-block and re-reads W.  Right-looking is chosen only when the model
+// predicts a clear win, so that a full-size projection on one GPU keeps the single-launch kernel.
+bool exact_prefers_right_looking(int d_row, int d_col) {
+    int sms = 148;
+    {
+        static int cached = 0;
+        if (!cached) {
+            int dev = 0, n = 0;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+                cached = n;
+            else
+                cached = 148;
+        }
+        sms = cached;
+    }
+    const double G = (double)((d_row + R - 1) / R), nsb = (double)(d_col / GQ_QK_K);
+    const double t_panel = 90.0, t_win = 14.6, t_launch = 8.0;
+    const double waves = ceil(G / sms);
+    const double left = waves * (nsb * t_panel + t_win * nsb * (nsb - 1.0) / 2.0);
+    double right = nsb * (waves * t_panel + t_launch);
+    for (int t = 1; t < (int)nsb; ++t) right += ceil(G * t / sms) * t_win;
+    return right < 0.8 * left;
+}
+
 }  // namespace
 
 void gq_fill_search_params(SearchParams &sp, int maxq, double rmin, double rdelta, int nstep);
@@ -452,7 +535,7 @@ void gq_fill_search_params(SearchParams &sp, int maxq, double rmin, double rdelt
 // ---- optional kernel-level profiling of the fast path (bench.py: rank-k GEMM time measured live with CUDA events) ----
 #include <vector>
 namespace {
-struct ProfEvent { cudaEvent_t a, b; int kind; };   // kind 0 = fused search/column-loop kernel, 1 = tcgen05 rank-k GEMM
+struct ProfEvent { cudaEvent_t a, b; int kind; };   // kind 0 = fused search/column-loop kernel, 1 = rank-k update launch (tcgen05 GEMM / exact_update_kernel)
 bool g_prof_on = false;
 std::vector<ProfEvent> g_prof;
 struct ProfScope {
@@ -509,10 +592,39 @@ size_t fast_ws_bytes(int d_row, int d_col) {
 
 template <int QT> int run_layer(LayerParams p, int mode, void *ws, size_t ws_bytes, cudaStream_t st) {
     const int nsb = p.d_col / GQ_QK_K;
-    p.fast = 0; p.e_hi = p.e_lo = nullptr; p.sb_begin = 0; p.sb_end = nsb;
-    if (mode == GQ_MODE_EXACT) {
-        ProfScope ps(st, 0);
-        return launch_layer<QT>(p, st);
+    p.fast = 0; p.skip_bulk = 0; p.e_hi = p.e_lo = nullptr; p.sb_begin = 0; p.sb_end = nsb;
+    if (mode != GQ_MODE_FAST) {
+        // Two bit-identical schedules of the exact arithmetic: ONE left-looking launch (each CTA applies all earlier
+        // blocks to its own tile), or per super-block a panel launch + exact_update_kernel over the whole trailing part.
+        bool right = mode == GQ_MODE_EXACT_RIGHT;
+        if (mode == GQ_MODE_EXACT) {
+            static int forced = -1;      // GQ_EXACT_SCHEDULE=left|right overrides the cost model (ablation runs)
+            if (forced < 0) {
+                const char *e = getenv("GQ_EXACT_SCHEDULE");
+                forced = (e && e[0] == 'l') ? 1 : (e && e[0] == 'r') ? 2 : 0;
+            }
+            right = forced == 2 || (forced == 0 && exact_prefers_right_looking(p.d_row, p.d_col));
+        }
+        if (!right || nsb < 2) {
+            ProfScope ps(st, 0);
+            return launch_layer<QT>(p, st);
+        }
+        p.skip_bulk = 1;
+        for (int sb = 0; sb < nsb; ++sb) {
+            p.sb_begin = sb; p.sb_end = sb + 1;
+            int rc;
+            {
+                ProfScope ps(st, 0);
+                rc = launch_layer<QT>(p, st);
+            }
+            if (rc) return rc;
+            {
+                ProfScope ps(st, 1);
+                rc = launch_exact_update(p, sb * GQ_QK_K, st);
+            }
+            if (rc) return rc;
+        }
+        return GQ_OK;
     }
     // ---- GQ_MODE_FAST: right-looking at super-block granularity.  Per 256-column super-block one launch of the fused
     // search / column-loop kernel, then ONE tcgen05 3xTF32 GEMM  W[:, c+256:] -= E[:, c:c+256] * U[c:c+256, c+256:].
@@ -528,7 +640,7 @@ template <int QT> int run_layer(LayerParams p, int mode, void *ws, size_t ws_byt
     GQ_CHECK_CUDA(cudaMemsetAsync(e_hi, 0, 2 * (size_t)mp * 256 * sizeof(float), st));   // padded rows stay zero
     transpose_split_kernel<<<dim3(n / 32, n / 32), 256, 0, st>>>(p.U, n, ut_hi, ut_lo);
     gq_count_launches(1);
-    p.fast = 1; p.e_hi = e_hi; p.e_lo = e_lo;
+    p.fast = 1; p.skip_bulk = 1; p.e_hi = e_hi; p.e_lo = e_lo;
     for (int sb = 0; sb < nsb; ++sb) {
         p.sb_begin = sb; p.sb_end = sb + 1;
         int rc;
@@ -576,14 +688,14 @@ extern "C" int gq_gptq_quantize_ex(float *W, const float *U, int d_row, int d_co
         gq_set_error("gq_gptq_quantize: block_size=%d not implemented (only 128, the run_quant.sh default)", block_size);
         return GQ_ERR_UNSUPPORTED;
     }
-    GQ_REQUIRE(mode == GQ_MODE_EXACT || mode == GQ_MODE_FAST, "gq_gptq_quantize: unknown mode %d", mode);
+    GQ_REQUIRE(mode >= GQ_MODE_EXACT && mode <= GQ_MODE_EXACT_RIGHT, "gq_gptq_quantize: unknown mode %d", mode);
     GQ_REQUIRE(static_groups >= 0 && static_groups <= 2, "gq_gptq_quantize: static_groups=%d must be 0, 1 or 2", static_groups);
     if (qtype == GQ_Q3_K) { static_groups = 0; perm = nullptr; }      // gptq.py:204-206: Q3_K ignores both options
     GQ_REQUIRE(perm == nullptr || static_groups == 2,
                "gq_gptq_quantize: act_order (perm) needs static_groups = 2 (scales searched on the un-permuted W beforehand)");
     GQ_REQUIRE(perm == nullptr || (packed == nullptr && wdeq == nullptr),
                "gq_gptq_quantize: with perm the codes come out in loop order; pack / dequantise after un-permuting them");
-    if ((static_groups || perm) && mode != GQ_MODE_EXACT) {
+    if ((static_groups || perm) && mode == GQ_MODE_FAST) {
         gq_set_error("gq_gptq_quantize: static_groups / act_order are implemented for GQ_MODE_EXACT only");
         return GQ_ERR_UNSUPPORTED;
     }

@@ -119,7 +119,8 @@ class Quantizer:
                  # ---- additions over the reference ----
                  calibration_batch_size: int = 8, share_hessians: bool = True, keep_results: bool = False,
                  save_packed: bool = True, timer: Optional[PhaseTimer] = None, early_exit_pass1: bool = True,
-                 overlap_prepare: bool = True, defer_last_layer: bool = True, fused_forward_ops: bool = True) -> None:
+                 overlap_prepare: bool = True, defer_last_layer: bool = True, fused_forward_ops: bool = True,
+                 early_prepare: bool = True) -> None:
         self.model = model
         self.data_loader = data_loader
         self.quantizable_modules = quantizable_modules
@@ -141,6 +142,7 @@ class Quantizer:
         self.overlap_prepare = overlap_prepare
         self.defer_last_layer = defer_last_layer
         self.fused_forward_ops = fused_forward_ops
+        self.early_prepare = early_prepare
         self.fused_installed: List[str] = []
         self._split_ok: Optional[bool] = None
         self._side_streams: list = []
@@ -208,17 +210,33 @@ class Quantizer:
         self._emit(name, q_type, (qweight, d, sq, dmin, zq), packed)
 
     # -------------------------------------------------------------------------------------------
-    def _prepare_hooks_and_handles(self, layers: Dict[str, nn.Module]):
+    def _prepare_hooks_and_handles(self, layers: Dict[str, nn.Module], quant_config=None, n_batches: int = 0):
         """quantizer.py:222-237, plus (a) Hessian sharing: layers that receive the very same input tensor object
         during a forward are attached to one accumulator, which is updated once per forward; (b) pass-1 early
         exit: the hooks are forward PRE-hooks (they see the same `inp[0]` as the reference's forward hooks), the
         first forward of a block records the order in which the hooked layers fire, and every later forward is
         interrupted (ForwardInterrupt) right after the last layer's Hessian update -- the reference discards the
-        output of pass 1 (quantizer.py:150-151), so the last projection's GEMM and the block tail are dead work."""
+        output of pass 1 (quantizer.py:150-151), so the last projection's GEMM and the block tail are dead work;
+        (c) early prepare: a Hessian is complete as soon as its update of the LAST calibration batch has been enqueued,
+        so the group's all-reduce, working copy and Cholesky chain (side stream) are started right there, inside the
+        hook, and run underneath the rest of that forward and the other layers' Hessian updates instead of after pass 1
+        (same kernels on the same inputs: bit-neutral)."""
         handles: Dict[str, GPTQ] = {}
         hooks = {}
         seen: list = []      # [(input tensor, accumulator)] of the forward in flight (refs keep addresses unique)
-        state = {"grouped": False, "order": [], "last": None, "fired": 0}
+        state = {"grouped": False, "order": [], "last": None, "fired": 0, "batch": 0, "early": {}}
+
+        def maybe_start_chain(h):
+            if not (self.early_prepare and self.overlap_prepare and quant_config is not None and state["grouped"]
+                    and n_batches > 1 and state["batch"] == n_batches - 1 and h.layer.weight.is_cuda):
+                return
+            groups = self._group_names(handles)
+            if len(groups) < 2 or id(h.hessian) in state["early"]:
+                return
+            for gi, names in enumerate(groups):
+                if handles[names[0]].hessian is h.hessian:
+                    state["early"][id(h.hessian)] = self._plan_group(gi, names, handles, quant_config, True)
+                    return
 
         def make_hook(name):
             def _hook(_, inp):
@@ -229,6 +247,7 @@ class Quantizer:
                     state["order"].append(name)
                 if not self.share_hessians:
                     h.update(x)
+                    maybe_start_chain(h)
                 else:
                     for t, acc in seen:
                         if t is x:
@@ -242,6 +261,7 @@ class Quantizer:
                     else:
                         h.update(x)
                         seen.append((x, h.hessian))
+                        maybe_start_chain(h)
                 if state["last"] == name and state["fired"] == len(handles):
                     raise ForwardInterrupt
             return _hook
@@ -259,20 +279,64 @@ class Quantizer:
                 if self.early_exit_pass1 and len(order) == len(handles) == len(set(order)) and order:
                     state["last"] = order[-1]
             state["fired"] = 0
+            state["batch"] += 1
 
         return handles, hooks, end_of_forward, state
 
+    @staticmethod
+    def _group_names(handles: Dict[str, GPTQ]) -> List[List[str]]:
+        """Layer names per shared HessianAccumulator, in module order."""
+        groups: Dict[int, List[str]] = {}
+        for name, h in handles.items():
+            groups.setdefault(id(h.hessian), []).append(name)
+        return list(groups.values())
+
+    def _plan_group(self, gi: int, names: List[str], handles: Dict[str, GPTQ], quant_config, overlap: bool):
+        """Phase A of one group (quantizer.py:242-255 up to the factor): all-reduce of H, stacked fp32 working copy,
+        dead-channel fix, Cholesky chain (on side stream `gi` when `overlap`).  Returns the plan tuple consumed by
+        _launch_group / _finish_group."""
+        kw = self.quantizer_kwargs
+        hs = [handles[n] for n in names]
+        acc = hs[0].hessian
+        with self.timer.span("allreduce"):
+            acc.all_reduce()                                               # gptq.py:131-132
+        rows = [h.d_row for h in hs]
+        with self.timer.span("prepare_host"):
+            # fp32 working copy of all members, stacked row-wise (gptq.py:138)
+            W = torch.cat([h.layer.weight.data.float() for h in hs], dim=0).contiguous()
+            ops.pre_step(acc.H, W)                                         # gptq.py:134-141
+            if len(hs) > 1:
+                masks = torch.stack([(w == 0).all(dim=0) for w in W.split(rows, dim=0)])
+                self._mask_flags.append((names, (masks != masks[0:1]).any()))   # checked at the end (no host sync here)
+            side = self._side_stream(gi) if overlap else None
+            # act_order (gptq.py:209-216): the loop runs on W[:, perm] with the factor of H[perm][:, perm]; Q3_K
+            # members ignore it (gptq.py:204-206) and need the plain factor
+            q3 = [quant_config.get(n.split(".")[-1], GGMLQuantizationType.Q4_K) == GGMLQuantizationType.Q3_K for n in names]
+            perm = U_perm = U = None
+            not_pd = []          # device flags (one per factorisation), read only at the end
+            if kw.get("act_order", False) and not all(q3):
+                perm = torch.argsort(torch.diag(acc.H), descending=True)
+                Hp = acc.H.index_select(0, perm).index_select(1, perm).contiguous()
+                U_perm, flag = ops.prepare(Hp, W.index_select(1, perm).contiguous(), kw.get("rel_damp", 1e-2),
+                                           stream=side, slot=1 + gi if overlap else 0)
+                not_pd.append(flag)
+            if perm is None or any(q3):
+                U, flag = ops.prepare(acc.H, W, kw.get("rel_damp", 1e-2), stream=side, slot=1 + gi if overlap else 0)  # gptq.py:305-324
+                not_pd.append(flag)
+            done = None
+            if side is not None:
+                done = torch.cuda.Event()
+                done.record(side)
+        return (names, hs, rows, W, U, not_pd, done, side, perm, U_perm)
+
     # -------------------------------------------------------------------------------------------
-    def _quant_group(self, handles: Dict[str, GPTQ], quant_config, defer: Optional[str] = None):
+    def _quant_group(self, handles: Dict[str, GPTQ], quant_config, defer: Optional[str] = None, early: Optional[dict] = None):
         """quantizer.py:242-275.  Handles are processed per shared accumulator; same-q_type members of a group are
         stacked row-wise into one launch, and with several ranks each rank takes a row slice.
         defer: name of a layer whose (single-layer) group is NOT finished here: its Cholesky chain AND its column loop
         are enqueued on the group's side stream and a callable is returned that, when called later on the main
         stream, waits for them, swaps the layer's weight and emits the result (see _deferred_tail_plan)."""
-        groups: Dict[int, List[str]] = {}
-        for name, h in handles.items():
-            groups.setdefault(id(h.hessian), []).append(name)
-        kw = self.quantizer_kwargs
+        groups = self._group_names(handles)
         rank, world = _rank(), _world()
         on_gpu = next(iter(handles.values())).layer.weight.is_cuda
         overlap = bool(self.overlap_prepare) and on_gpu and len(groups) > 1
@@ -282,45 +346,17 @@ class Quantizer:
         # With `overlap_prepare` every group's Cholesky chain runs on its own side stream (own workspace slot), so
         # the latency-bound chains of the 4 groups of a block run concurrently.  True / "eager": the main stream
         # waits only for the U it is about to consume, so later chains also overlap the column-loop kernels of the
-        # groups before them; "staged": all chains first, then the column loops.
+        # groups before them; "staged": all chains first, then the column loops.  Groups whose chain was already started
+        # from the forward hook of the last calibration batch (`early`) are taken as they are.
+        early = early or {}
         plans = []
-        for gi, names in enumerate(groups.values()):
-            hs = [handles[n] for n in names]
-            acc = hs[0].hessian
-            with self.timer.span("allreduce"):
-                acc.all_reduce()                                               # gptq.py:131-132
-            rows = [h.d_row for h in hs]
-            with self.timer.span("prepare_host"):
-                # fp32 working copy of all members, stacked row-wise (gptq.py:138)
-                W = torch.cat([h.layer.weight.data.float() for h in hs], dim=0).contiguous()
-                ops.pre_step(acc.H, W)                                         # gptq.py:134-141
-                if len(hs) > 1:
-                    masks = torch.stack([(w == 0).all(dim=0) for w in W.split(rows, dim=0)])
-                    self._mask_flags.append((names, (masks != masks[0:1]).any()))   # checked at the end (no host sync here)
-                side = self._side_stream(gi) if overlap else None
-                # act_order (gptq.py:209-216): the loop runs on W[:, perm] with the factor of H[perm][:, perm]; Q3_K
-                # members ignore it (gptq.py:204-206) and need the plain factor
-                q3 = [quant_config.get(n.split(".")[-1], GGMLQuantizationType.Q4_K) == GGMLQuantizationType.Q3_K for n in names]
-                perm = U_perm = U = None
-                not_pd = []          # device flags (one per factorisation), read only at the end
-                if kw.get("act_order", False) and not all(q3):
-                    perm = torch.argsort(torch.diag(acc.H), descending=True)
-                    Hp = acc.H.index_select(0, perm).index_select(1, perm).contiguous()
-                    U_perm, flag = ops.prepare(Hp, W.index_select(1, perm).contiguous(), kw.get("rel_damp", 1e-2),
-                                               stream=side, slot=1 + gi if overlap else 0)
-                    not_pd.append(flag)
-                if perm is None or any(q3):
-                    U, flag = ops.prepare(acc.H, W, kw.get("rel_damp", 1e-2), stream=side, slot=1 + gi if overlap else 0)  # gptq.py:305-324
-                    not_pd.append(flag)
-                done = None
-                if side is not None:
-                    done = torch.cuda.Event()
-                    done.record(side)
-            plans.append((names, hs, rows, W, U, not_pd, done, side, perm, U_perm))
+        for gi, names in enumerate(groups):
+            plan = early.get(id(handles[names[0]].hessian))
+            plans.append(plan if plan is not None else self._plan_group(gi, names, handles, quant_config, overlap))
         deferred = None
         if defer is not None:
             hit = [pl for pl in plans if pl[0] == [defer]]
-            if overlap and world == 1 and len(hit) == 1 and hit[0][7] is not None:
+            if overlap and len(hit) == 1 and hit[0][7] is not None:
                 deferred = hit[0]
                 plans = [pl for pl in plans if pl is not deferred]
         # ---- phase B: the column loops, in module order, on the main stream
@@ -401,20 +437,25 @@ class Quantizer:
                     mode={"exact": 0, "fast": 1}[kw.get("mode", "exact")], static_groups=static_groups, perm=perm)
         if world == 1:
             return ops.gptq_quantize(W, U, qt, stream=stream, **args)[:7]
+        # Row slice of this rank (in units of the kernel's 32-row CTA tile), then one all-gather per result tensor.
+        # Every buffer is allocated on the CURRENT stream; with `stream` (the deferred group's side stream) the column
+        # loop and the all-gathers are enqueued there -- torch's NCCL work waits for / is waited on by the stream that
+        # is current at the call, and every rank issues the collectives in the same host order.
         total = W.shape[0]
         per = -(-total // world)
-        per = -(-per // 32) * 32                     # row slices in units of the kernel's 32-row CTA tile
+        per = -(-per // 32) * 32
         lo, hi = min(rank * per, total), min((rank + 1) * per, total)
         Wl = torch.zeros(per, W.shape[1], dtype=W.dtype, device=W.device)
         Wl[: hi - lo] = W[lo:hi]
-        outs = ops.gptq_quantize(Wl, U, qt, **args)[:7]
-        with self.timer.span("allgather"):
-            full = []
-            for t in outs:
-                g = torch.empty((world * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-                dist.all_gather_into_tensor(g, t.contiguous())
-                full.append(g[:total])
-        return tuple(full)
+        outs = ops.gptq_quantize(Wl, U, qt, stream=stream, **args)[:7]
+        full = [torch.empty((world * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for t in outs]
+        if stream is not None:
+            stream.wait_stream(torch.cuda.current_stream(W.device))      # the gather buffers were allocated on the main stream
+        with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
+            with self.timer.span("allgather"):
+                for g, t in zip(full, outs):
+                    dist.all_gather_into_tensor(g, t.contiguous())
+        return tuple(g[:total] for g in full)
 
     # -------------------------------------------------------------------------------------------
     def _deferred_tail_plan(self, block, layers, hook_state, batches, device):
@@ -424,7 +465,7 @@ class Quantizer:
         operation is the last quantised layer (down_proj) and `residual` is the input of `post_attention_layernorm`.
         That structure is not assumed but CHECKED once, on the first calibration batch of the first block: the output
         of the plain `block(...)` call must equal `residual + last(x)` bit for bit, otherwise the generic path is kept."""
-        if not (self.defer_last_layer and self.overlap_prepare and _world() == 1 and not self.cpu_offload_activations):
+        if not (self.defer_last_layer and self.overlap_prepare and not self.cpu_offload_activations):
             return None
         last_name = hook_state.get("last")
         norm = getattr(block, "post_attention_layernorm", None)
@@ -570,7 +611,7 @@ class Quantizer:
             block = block.to(device)
             layer_prefix = f"{self.block_modules}.{block_id}."
             layers = select_layers(self.model, layer_prefix, self.quantizable_modules, LINEAR_LAYERS)
-            handles, hooks, end_of_forward, hook_state = self._prepare_hooks_and_handles(layers)
+            handles, hooks, end_of_forward, hook_state = self._prepare_hooks_and_handles(layers, quant_config, len(batches))
 
             with self.timer.span("forward1"):
                 for inp_args, inp_kwargs in batches:
@@ -583,7 +624,8 @@ class Quantizer:
                 h.remove()
 
             tail = self._deferred_tail_plan(block, layers, hook_state, batches, device)
-            finish = self._quant_group(handles, quant_config, defer=tail["last_name"] if tail else None)
+            finish = self._quant_group(handles, quant_config, defer=tail["last_name"] if tail else None,
+                                       early=hook_state.get("early"))
 
             if finish is None:
                 with self.timer.span("forward2"):

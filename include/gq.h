@@ -53,8 +53,13 @@ typedef enum { GQ_Q2_K = 10, GQ_Q3_K = 11, GQ_Q4_K = 12, GQ_Q5_K = 13, GQ_Q6_K =
 typedef enum { GQ_F32 = 0, GQ_F16 = 1, GQ_BF16 = 2 } gq_dtype;
 
 /* GQ_MODE_EXACT reproduces the reference's CPU arithmetic bit for bit given the same (W, U).
- * GQ_MODE_FAST runs the rank-k update on tcgen05 tensor cores (3xTF32); not bit-identical. */
-typedef enum { GQ_MODE_EXACT = 0, GQ_MODE_FAST = 1 } gq_mode;
+ * GQ_MODE_FAST runs the rank-k update on tcgen05 tensor cores (3xTF32); not bit-identical.
+ * The exact arithmetic has two bit-identical schedules: ONE left-looking launch per layer (every 32-row CTA applies all
+ * earlier blocks to its own tile), and a right-looking one (per 256-column super-block a panel launch + an exact FFMA
+ * update of the whole trailing part by all SMs) that wins when a launch has few rows and many columns (a row slice of
+ * down_proj on one of several GPUs).  GQ_MODE_EXACT picks by a cost model (environment GQ_EXACT_SCHEDULE=left|right
+ * overrides it); GQ_MODE_EXACT_LEFT / GQ_MODE_EXACT_RIGHT force one (tests compare both with the goldens). */
+typedef enum { GQ_MODE_EXACT = 0, GQ_MODE_FAST = 1, GQ_MODE_EXACT_LEFT = 2, GQ_MODE_EXACT_RIGHT = 3 } gq_mode;
 
 typedef void *gq_stream_t;
 
@@ -108,8 +113,9 @@ GQ_API int gq_prepare(float *H, const float *W, int d_row, int d_col, float rel_
  *          never skips, so (flags[2s+1] & ~flags[2s]) != 0 marks the (degenerate) inputs on which the
  *          two can differ.  Must be zero-initialised by the caller.
  * block_size must be 128 (the reference's run_quant.sh default).
- * mode GQ_MODE_FAST needs gq_gptq_workspace_bytes() of scratch (GQ_MODE_EXACT needs none): the rank-k updates between
- * 256-column super-blocks then run as tcgen05 3xTF32 GEMMs (fp32-class accuracy, NOT bit-identical to the reference). */
+ * mode GQ_MODE_FAST needs gq_gptq_workspace_bytes() of scratch (the exact modes need none): the rank-k updates between
+ * 256-column super-blocks then run as tcgen05 3xTF32 GEMMs (fp32-class accuracy, NOT bit-identical to the reference).
+ * GQ_MODE_EXACT / _LEFT / _RIGHT give bit-identical outputs (see gq_mode); they differ in the number of launches. */
 GQ_API size_t gq_gptq_workspace_bytes(int d_row, int d_col, int mode);
 GQ_API int gq_gptq_quantize(float *W, const float *U, int d_row, int d_col, int qtype, int block_size,
                      double rmin, double rdelta, int nstep, int mode,
@@ -118,7 +124,7 @@ GQ_API int gq_gptq_quantize(float *W, const float *U, int d_row, int d_col, int 
                      void *workspace, size_t ws_bytes, gq_stream_t stream);
 
 /* gq_gptq_quantize with the reference's two optional variants of GPTQ.step (gptq.py:184-216, 233-238, 273-277;
- * GQ_MODE_EXACT only; Q3_K ignores both, gptq.py:204-206):
+ * exact modes only; Q3_K ignores both, gptq.py:204-206):
  *   static_groups = 0  scales searched per super-block on the live weights (gq_gptq_quantize);
  *                 = 1  all scales / zeros searched up front on W as passed (gptq.py:184-196);
  *                 = 2  d, dmin, sq, zq already hold them on entry (the caller ran gq_get_scale_and_zero on the 256-column

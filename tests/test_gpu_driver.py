@@ -1,6 +1,7 @@
 """GPU: the block-sequential driver (gptq_gguf_toolkit_b200/quantizer.py) on a tiny random Llama, through libgq.
 
-The scheduling options added over the reference -- pass-1 early exit, Cholesky chains on side streams (eager / staged),
+The scheduling options added over the reference -- pass-1 early exit, Cholesky chains on side streams (eager / staged;
+started from the forward hook of the last calibration batch or after pass 1),
 the deferred-tail split of pass 2 (last quantised layer's chain + column loop overlapped with the block forwards) --
 must not change a single bit of any result: same kernels, same inputs, only the order of independent work differs."""
 import pytest
@@ -48,6 +49,7 @@ def test_scheduling_options_are_bit_neutral(dtype):
         "staged": dict(overlap_prepare="staged"),
         "eager, no deferred tail": dict(defer_last_layer=False),
         "no early exit": dict(early_exit_pass1=False),
+        "no early prepare (chains start after pass 1)": dict(early_prepare=False),
     }
     for name, kw in variants.items():
         model, q = _run(dtype, **kw)
