@@ -224,11 +224,12 @@ class Quantizer:
         handles: Dict[str, GPTQ] = {}
         hooks = {}
         seen: list = []      # [(input tensor, accumulator)] of the forward in flight (refs keep addresses unique)
-        state = {"grouped": False, "order": [], "last": None, "fired": 0, "batch": 0, "early": {}}
+        state = {"grouped": False, "order": [], "last": None, "fired": 0, "batch": 0, "early": {}, "simple": False}
 
         def maybe_start_chain(h):
+            # state["simple"]: every hooked layer fired exactly once in the recorded forward (one update per batch)
             if not (self.early_prepare and self.overlap_prepare and quant_config is not None and state["grouped"]
-                    and n_batches > 1 and state["batch"] == n_batches - 1 and h.layer.weight.is_cuda):
+                    and state["simple"] and n_batches > 1 and state["batch"] == n_batches - 1 and h.layer.weight.is_cuda):
                 return
             groups = self._group_names(handles)
             if len(groups) < 2 or id(h.hessian) in state["early"]:
@@ -275,8 +276,9 @@ class Quantizer:
             if not state["grouped"]:
                 state["grouped"] = True
                 order = state["order"]
+                state["simple"] = bool(order) and len(order) == len(handles) == len(set(order))
                 # early exit only when every hooked layer fired exactly once in the recorded forward
-                if self.early_exit_pass1 and len(order) == len(handles) == len(set(order)) and order:
+                if self.early_exit_pass1 and state["simple"]:
                     state["last"] = order[-1]
             state["fired"] = 0
             state["batch"] += 1

@@ -62,9 +62,12 @@ def main():
         for n in (4096, 14336):
             H0 = spd(n)
             W = torch.randn(256, n, device="cuda")
-            l0 = ops.launch_count()
-            mn, av = timed(lambda: ops.prepare(H0.clone(), W, 0.01), warm=1, it=2)
-            print(f"prepare n={n}: {mn:.2f} ms (avg {av:.2f}), launches/call {(ops.launch_count() - l0) // 3}", flush=True)
+            for v in ("1", "0"):        # chol_diag_v2_kernel (default) vs the original diagonal kernel
+                os.environ["GQ_DIAG_V2"] = v
+                l0 = ops.launch_count()
+                mn, av = timed(lambda: ops.prepare(H0.clone(), W, 0.01), warm=1, it=2)
+                print(f"prepare n={n} GQ_DIAG_V2={v}: {mn:.2f} ms (avg {av:.2f}), launches/call {(ops.launch_count() - l0) // 3}", flush=True)
+            os.environ["GQ_DIAG_V2"] = "1"
     if "hessian" in what:
         for n, T in ((4096, 16384), (14336, 16384)):
             X = torch.randn(T, n, device="cuda").to(torch.bfloat16)
@@ -89,6 +92,17 @@ def main():
             ops.profile_enable(False)
             print(f"gptq FAST {rows}x{n}: {mn:.2f} ms -> rank-k {fl / mn / 1e9:.1f} TFLOP/s; panel {pr['panel_ms']:.2f} ms/{pr['panel_launches']}, "
                   f"tcgen05 rank-k GEMMs {pr['rankk_gemm_ms']:.2f} ms/{pr['rankk_gemm_launches']} -> {rows * n * (n - 256) / max(pr['rankk_gemm_ms'], 1e-9) / 1e9:.0f} TFLOP/s", flush=True)
+    if "schedules" in what:
+        # the two bit-identical schedules of the exact arithmetic on row slices (what one rank of an N-GPU run launches)
+        for rows, n in ((4096, 14336), (2048, 14336), (1024, 14336), (512, 14336), (4096, 4096), (512, 4096), (3584, 4096), (768, 4096)):
+            U = torch.triu(torch.randn(n, n, device="cuda") * 0.01) + torch.eye(n, device="cuda")
+            W0 = torch.randn(rows, n, device="cuda") * 0.02
+            res = {}
+            for name, mode in (("auto", 0), ("left", 2), ("right", 3)):
+                mn, _ = timed(lambda: ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16, mode=mode), warm=1, it=2)
+                res[name] = mn
+            print(f"schedules {rows}x{n}: " + ", ".join(f"{k} {v:.2f} ms" for k, v in res.items()), flush=True)
+            del U, W0
     if "rtn" in what:
         W = torch.randn(128256, 4096, device="cuda").to(torch.bfloat16)
         mn, av = timed(lambda: ops.rtn_quantize(W, 12, wdeq_dtype=torch.bfloat16), warm=1, it=2)

@@ -259,8 +259,16 @@ def _spd_problem(n, d_row, seed):
     return H, W
 
 
-@pytest.mark.parametrize("n", [128, 384, 896])
-def test_prepare_matches_double_precision(ops, n):
+@pytest.fixture(params=["1", "0"], ids=["diag_v2", "diag_v1"])
+def diag_variant(request, monkeypatch):
+    """Both diagonal-block kernels of gq_prepare (csrc/linalg.cu: chol_diag_v2_kernel, the default, and the original
+    chol_diag_kernel) must meet the same B2 bounds; the library reads GQ_DIAG_V2 on every call."""
+    monkeypatch.setenv("GQ_DIAG_V2", request.param)
+    return request.param
+
+
+@pytest.mark.parametrize("n", [128, 384, 896, 2048])
+def test_prepare_matches_double_precision(ops, n, diag_variant):
     H, W = _spd_problem(n, 16, n)
     W[:, 7] = 0.0                              # an all-zero weight column (gptq.py:308-313)
     Hd, Wd = dev(H), dev(W)
@@ -279,7 +287,7 @@ def test_prepare_matches_double_precision(ops, n):
     assert np.abs(got - inv).max() <= 5e-4 * np.abs(inv).max()
 
 
-def test_prepare_not_positive_definite_falls_back_to_identity(ops):
+def test_prepare_not_positive_definite_falls_back_to_identity(ops, diag_variant):
     n = 256
     H = -np.eye(n, dtype=np.float32)
     W = np.ones((8, n), np.float32)
