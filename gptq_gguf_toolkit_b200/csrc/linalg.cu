@@ -191,25 +191,67 @@ __global__ void __launch_bounds__(DT2) chol_diag_v2_kernel(float *A, float *Binv
                 s.inv[col] = iv;
                 if (bad) *not_pd = 1;
             }
-            // L: rows below col, the panel's columns right of col:  L[i][c] -= l_i,col * l_c,col   (operands scaled on the fly)
-            {
+            // Warps 0..7 update L, warps 8..15 update X (every warp executes one region's instructions only: with 16
+            // warps the sweep is issue-bound, not latency-bound, if each warp walks through predicated-off code).
+            // All loads of a trip are issued before its first store: the compiler cannot move a shared-memory load
+            // across a store that might alias, and a load -> FMA -> store chain per element would serialise the sweep.
+            if (w < NW / 2) {
+                // L: rows below col, the panel's columns right of col:  L[i][c] -= l_i,col * l_c,col   (operands scaled on the fly)
                 const int c = base + lane;
                 if (c > col) {
                     const float lc = __fmul_rn(s.L[c * LS + col], iv);
-#pragma unroll 4
-                    for (int i = col + 1 + w; i < NB; i += NW) {
-                        if (c <= i) {
-                            const float li = __fmul_rn(s.L[i * LS + col], iv);
-                            s.L[i * LS + c] = __fmaf_rn(-li, lc, s.L[i * LS + c]);
+#pragma unroll 1
+                    for (int i0 = col + 1 + w; i0 < NB; i0 += 2 * NW) {      // rows i0, i0+8, i0+16, i0+24
+                        float li[4], t[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + (NW / 2) * u;
+                            if (i < NB && c <= i) { li[u] = s.L[i * LS + col]; t[u] = s.L[i * LS + c]; }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + (NW / 2) * u;
+                            if (i < NB && c <= i) s.L[i * LS + c] = __fmaf_rn(-__fmul_rn(li[u], iv), lc, t[u]);
                         }
                     }
                 }
-            }
-            // X: the panel's rows below col:  X[i][0..col] -= l_i,col * x_col,:
-            for (int i = col + 1 + w; i < base + PW; i += NW) {
-                const float li = __fmul_rn(s.L[i * LS + col], iv);
-                for (int cc = lane; cc <= col; cc += 32)
-                    s.X[i * LS + cc] = __fmaf_rn(-li, __fmul_rn(s.X[col * LS + cc], iv), s.X[i * LS + cc]);
+            } else {
+                // X: the panel's rows below col:  X[i][0..col] -= l_i,col * x_col,:
+                const int w2 = w - NW / 2, nq = (col >> 5) + 1;
+                float xs[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int cc = lane + 32 * q;
+                    xs[q] = (q < nq && cc <= col) ? __fmul_rn(s.X[col * LS + cc], iv) : 0.0f;
+                }
+#pragma unroll 1
+                for (int i0 = col + 1 + w2; i0 < base + PW; i0 += NW) {        // rows i0, i0+8
+                    float xi[2][4], li[2];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const int i = i0 + (NW / 2) * r;
+                        if (i < base + PW) {
+                            li[r] = s.L[i * LS + col];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int cc = lane + 32 * q;
+                                if (q < nq && cc <= col) xi[r][q] = s.X[i * LS + cc];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const int i = i0 + (NW / 2) * r;
+                        if (i < base + PW) {
+                            const float l = __fmul_rn(li[r], iv);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int cc = lane + 32 * q;
+                                if (q < nq && cc <= col) s.X[i * LS + cc] = __fmaf_rn(-l, xs[q], xi[r][q]);
+                            }
+                        }
+                    }
+                }
             }
         }
         __syncthreads();

@@ -319,8 +319,11 @@ class Quantizer:
             if kw.get("act_order", False) and not all(q3):
                 perm = torch.argsort(torch.diag(acc.H), descending=True)
                 Hp = acc.H.index_select(0, perm).index_select(1, perm).contiguous()
-                U_perm, flag = ops.prepare(Hp, W.index_select(1, perm).contiguous(), kw.get("rel_damp", 1e-2),
-                                           stream=side, slot=1 + gi if overlap else 0)
+                Wp = W.index_select(1, perm).contiguous()
+                if side is not None:      # temporaries of this function that the side stream still has to read
+                    Hp.record_stream(side)
+                    Wp.record_stream(side)
+                U_perm, flag = ops.prepare(Hp, Wp, kw.get("rel_damp", 1e-2), stream=side, slot=1 + gi if overlap else 0)
                 not_pd.append(flag)
             if perm is None or any(q3):
                 U, flag = ops.prepare(acc.H, W, kw.get("rel_damp", 1e-2), stream=side, slot=1 + gi if overlap else 0)  # gptq.py:305-324
@@ -452,6 +455,12 @@ class Quantizer:
         outs = ops.gptq_quantize(Wl, U, qt, stream=stream, **args)[:7]
         full = [torch.empty((world * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for t in outs]
         if stream is not None:
+            # Wl and the per-rank outputs die when this function returns, long before the side stream has run the kernel
+            # and the all-gathers that use them: tell the caching allocator (otherwise the main stream's next allocations
+            # -- the pass-2 activations -- would reuse the memory underneath the pending kernels).
+            for t in (Wl,) + tuple(outs):
+                if t is not None:
+                    t.record_stream(stream)
             stream.wait_stream(torch.cuda.current_stream(W.device))      # the gather buffers were allocated on the main stream
         with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
             with self.timer.span("allgather"):

@@ -94,7 +94,7 @@ def main():
                   f"tcgen05 rank-k GEMMs {pr['rankk_gemm_ms']:.2f} ms/{pr['rankk_gemm_launches']} -> {rows * n * (n - 256) / max(pr['rankk_gemm_ms'], 1e-9) / 1e9:.0f} TFLOP/s", flush=True)
     if "schedules" in what:
         # the two bit-identical schedules of the exact arithmetic on row slices (what one rank of an N-GPU run launches)
-        for rows, n in ((4096, 14336), (2048, 14336), (1024, 14336), (512, 14336), (4096, 4096), (512, 4096), (3584, 4096), (768, 4096)):
+        for rows, n in ((4096, 14336), (2048, 14336), (1024, 14336), (512, 14336), (4096, 4096), (512, 4096), (28672, 4096), (14336, 4096), (3584, 4096), (6144, 4096), (3072, 4096), (768, 4096)):
             U = torch.triu(torch.randn(n, n, device="cuda") * 0.01) + torch.eye(n, device="cuda")
             W0 = torch.randn(rows, n, device="cuda") * 0.02
             res = {}
