@@ -90,13 +90,16 @@ struct __align__(16) Smem {
     float gzr[R * 16];
     float dg_b[128];                         // diagonal of the current U block and its checked reciprocal (DivBy)
     float dg_y[128];
-    float pc_sc[R * 128];                    // act_order: per (row, column of the block) scale, zero, checked 1/scale
-    float pc_zz[R * 128];
-    float pc_y[R * 128];
     float dummy_f[64];                       // sink of the non-owner lanes' stores in the serial phase
     uint8_t dummy_b[32];
     RowScales<R> rs;
+    // act_order only -- kept LAST: launches without a permutation allocate the struct up to here (SMEM_NO_PERM), which
+    // lets two panel CTAs share an SM in the right-looking schedule
+    float pc_sc[R * 128];                    // per (row, column of the block) scale, zero, checked 1/scale
+    float pc_zz[R * 128];
+    float pc_y[R * 128];
 };
+constexpr size_t SMEM_NO_PERM = offsetof(Smem, pc_sc);
 
 // Shared-memory layout of the (128 x 128) diagonal block of U for the serial phase: in row i the 16 values a
 // lane (l8 = j & 7) needs -- columns j = 8s + l8 -- are contiguous (64 B), 16-byte chunks XOR-swizzled by (l8 >> 1) & 3
@@ -277,8 +280,12 @@ __device__ __forceinline__ void serial_block(Smem &sm, int blk, int warp, int la
     for (int s = 0; s < 16; ++s) sm.Wt[wt_idx(srow, blk * 128 + 8 * s + l8)] = sm.Wq[srow * 128 + 8 * s + l8];
 }
 
-template <int QT>
-__global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) {
+// MINB = 1: the full kernel (left-looking bulk update inside, 255 registers).  MINB = 2: register-capped build for the
+// panel launches of the exact right-looking schedule (skip_bulk, no permutation): the search and the 256 dependent column
+// steps are latency-bound, so two co-resident CTAs per SM (128 registers, SMEM_NO_PERM bytes each) overlap their stalls
+// and halve the number of CTA waves of a launch.
+template <int QT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) gptq_layer_kernel(const LayerParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     constexpr int GS = Fmt<QT>::GS, GPR = GQ_QK_K / GS;
@@ -443,10 +450,19 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
 }
 
 template <int QT> int launch_layer(const LayerParams &p, cudaStream_t st) {
-    const size_t smem = sizeof(Smem);
-    GQ_CHECK_CUDA(cudaFuncSetAttribute(gptq_layer_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (p.d_row + R - 1) / R;
-    gptq_layer_kernel<QT><<<grid, NT, smem, st>>>(p);
+    static int two_ok = -1;      // GQ_PANEL_2CTA=0 switches the two-CTAs-per-SM panel build off (ablation)
+    if (two_ok < 0) { const char *e = getenv("GQ_PANEL_2CTA"); two_ok = (e && e[0] == '0') ? 0 : 1; }
+    if (two_ok && p.skip_bulk && !p.fast && p.perm == nullptr) {
+        GQ_CHECK_CUDA(cudaFuncSetAttribute(gptq_layer_kernel<QT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_NO_PERM));
+        gptq_layer_kernel<QT, 2><<<grid, NT, SMEM_NO_PERM, st>>>(p);
+        gq_count_launches(1);
+        GQ_CHECK_CUDA(cudaGetLastError());
+        return GQ_OK;
+    }
+    const size_t smem = p.perm == nullptr ? SMEM_NO_PERM : sizeof(Smem);
+    GQ_CHECK_CUDA(cudaFuncSetAttribute(gptq_layer_kernel<QT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    gptq_layer_kernel<QT, 1><<<grid, NT, smem, st>>>(p);
     gq_count_launches(1);
     GQ_CHECK_CUDA(cudaGetLastError());
     return GQ_OK;
@@ -501,31 +517,15 @@ int launch_exact_update(const LayerParams &p, int c, cudaStream_t st) {
     return GQ_OK;
 }
 
-// Which exact schedule is faster?  A cost model in microseconds fitted to the measured kernel (profiles/r01_ncu_summary.md:
-// ~90 us of search + column steps per super-block and CTA wave, ~14.6 us of FFMA rank-k work per (32 x 256) window and
-// earlier super-block); the left-looking kernel pays the rank-k work serially inside each CTA, the right-looking schedule
-// spreads it over all SMs but launches twice per super-block and re-reads W.  Right-looking is chosen only when the model
-// predicts a clear win, so that a full-size projection on one GPU keeps the single-launch kernel.
+// Which exact schedule?  Measured on B200 (profiles/r01_schedules.md, Q4_K, both bit-identical): the right-looking
+// schedule wins at every Llama-3-8B shape -- 28672 x 4096: 19.6 vs 21.5 ms, 4096 x 14336: 24.2 vs 27.9 ms, and by 2-3.5x on
+// the row slices a rank of a multi-GPU run launches (512 x 14336: 7.7 vs 27.2 ms) -- because the trailing update runs
+// with two co-resident CTAs per SM and no idle tail wave, while the left-looking kernel does it inside one 255-register
+// CTA per SM.  The single left-looking launch is kept for narrow layers (fewer than 4 super-blocks), where two launches
+// per super-block buy nothing.
 bool exact_prefers_right_looking(int d_row, int d_col) {
-    int sms = 148;
-    {
-        static int cached = 0;
-        if (!cached) {
-            int dev = 0, n = 0;
-            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-                cached = n;
-            else
-                cached = 148;
-        }
-        sms = cached;
-    }
-    const double G = (double)((d_row + R - 1) / R), nsb = (double)(d_col / GQ_QK_K);
-    const double t_panel = 90.0, t_win = 14.6, t_launch = 8.0;
-    const double waves = ceil(G / sms);
-    const double left = waves * (nsb * t_panel + t_win * nsb * (nsb - 1.0) / 2.0);
-    double right = nsb * (waves * t_panel + t_launch);
-    for (int t = 1; t < (int)nsb; ++t) right += ceil(G * t / sms) * t_win;
-    return right < 0.8 * left;
+    (void)d_row;
+    return d_col / GQ_QK_K >= 4;
 }
 
 }  // namespace
