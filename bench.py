@@ -243,6 +243,8 @@ def main():
     ap.add_argument("--no-defer", action="store_true", help="ablation: no split of forward pass 2 at the last quantised layer")
     ap.add_argument("--no-fused-forward", action="store_true", help="ablation: HF's eager RMSNorm / rotary / SiLU*up kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--compare-left", type=int, default=0, metavar="K",
+                    help="ablation: K extra steps with the exact LEFT-looking schedule (one launch per layer), same process")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
 
@@ -353,6 +355,14 @@ def main():
         for k in prof:
             prof[k] = prof[k] / args.steps
 
+    left = None
+    if args.compare_left > 0 and main_mode == "exact":
+        one_step(False, "exact_left")
+        lt = [one_step(False, "exact_left") for _ in range(args.compare_left)]
+        left = {"value": sum(t[0] for t in lt) / len(lt), "unit": "s", "steps": args.compare_left,
+                "phases_s": {k: round(v, 4) for k, v in sorted(lt[-1][1].items())},
+                "note": "GQ_MODE_EXACT_LEFT: one left-looking launch per layer; bit-identical outputs"}
+
     fast = None
     if args.mode == "both":
         # one extra step with the tcgen05 rank-k path; CUDA events around every rank-k GEMM launch (gq_profile_*)
@@ -385,12 +395,12 @@ def main():
                 "traffic": EXACT_UPDATE_DRAM_BYTES, "traffic_note": EXACT_UPDATE_TRAFFIC_NOTE,
                 "kernel": "exact_update_kernel: rank-256 trailing update of the exact right-looking schedule, W[:, c+256:] -= "
                           "E[:, c:c+256] U[c:c+256, c+256:] as two sequentially rounded 128-term fp32 FMA chains per element",
-                "launches_per_step": prof["rankk_gemm_launches"], "avg_launch_ms": prof["rankk_gemm_ms"] / max(1, prof["rankk_gemm_launches"]),
+                "launches_per_step": int(round(prof["rankk_gemm_launches"])), "avg_launch_ms": prof["rankk_gemm_ms"] / max(1, prof["rankk_gemm_launches"]),
                 "total_ms_per_step": prof["rankk_gemm_ms"], "algorithmic_flops_per_step": upd_flops,
                 "peak_source": pk["source"],
                 "simt_fp32_peak_tflops": round(simt_peak, 1), "frac_of_simt_fp32_peak": achieved / simt_peak,
                 "panel_kernel": {"name": "gptq_layer_kernel<Q4_K> (scale search + 256 column steps + in-super-block update + GGUF pack, "
-                                         "one launch per super-block)", "launches_per_step": prof["panel_launches"],
+                                         "one launch per super-block)", "launches_per_step": int(round(prof["panel_launches"])),
                                  "total_ms_per_step": prof["panel_ms"]},
                 "note": ("CUDA events around every launch, on the launching stream, inside the timed steps; "
                          "down_proj's launches run on a side stream concurrently with the pass-2 block forwards, which "
@@ -424,6 +434,8 @@ def main():
             "clocks": clocks,
             "non_invertible_modules": bad,
         }
+        if left is not None:
+            line["left_looking_schedule"] = left
         if fast is not None:
             secs_f, ph_f, pr = fast
             # the GEMMs cover d_row*d_col*(d_col-256) of the rank-k flops (the first 128 columns' update of each

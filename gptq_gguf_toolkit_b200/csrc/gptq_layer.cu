@@ -93,8 +93,7 @@ struct __align__(16) Smem {
     float dummy_f[64];                       // sink of the non-owner lanes' stores in the serial phase
     uint8_t dummy_b[32];
     RowScales<R> rs;
-    // act_order only -- kept LAST: launches without a permutation allocate the struct up to here (SMEM_NO_PERM), which
-    // lets two panel CTAs share an SM in the right-looking schedule
+    // act_order only -- kept LAST: launches without a permutation allocate the struct up to here (SMEM_NO_PERM)
     float pc_sc[R * 128];                    // per (row, column of the block) scale, zero, checked 1/scale
     float pc_zz[R * 128];
     float pc_y[R * 128];
@@ -280,12 +279,11 @@ __device__ __forceinline__ void serial_block(Smem &sm, int blk, int warp, int la
     for (int s = 0; s < 16; ++s) sm.Wt[wt_idx(srow, blk * 128 + 8 * s + l8)] = sm.Wq[srow * 128 + 8 * s + l8];
 }
 
-// MINB = 1: the full kernel (left-looking bulk update inside, 255 registers).  MINB = 2: register-capped build for the
-// panel launches of the exact right-looking schedule (skip_bulk, no permutation): the search and the 256 dependent column
-// steps are latency-bound, so two co-resident CTAs per SM (128 registers, SMEM_NO_PERM bytes each) overlap their stalls
-// and halve the number of CTA waves of a launch.
-template <int QT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) gptq_layer_kernel(const LayerParams p) {
+// (A register-capped build of this kernel for the panel launches of the right-looking schedule -- __launch_bounds__(256, 2),
+// 128 registers, two co-resident CTAs per SM -- was measured on B200 and was 3-5 % SLOWER at every shape: the K-quant search
+// of the 32-weight-group types spills, and the column steps lose the registers that keep their loads ahead of the chain.)
+template <int QT>
+__global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     constexpr int GS = Fmt<QT>::GS, GPR = GQ_QK_K / GS;
@@ -451,18 +449,9 @@ __global__ void __launch_bounds__(NT, MINB) gptq_layer_kernel(const LayerParams 
 
 template <int QT> int launch_layer(const LayerParams &p, cudaStream_t st) {
     const int grid = (p.d_row + R - 1) / R;
-    static int two_ok = -1;      // GQ_PANEL_2CTA=0 switches the two-CTAs-per-SM panel build off (ablation)
-    if (two_ok < 0) { const char *e = getenv("GQ_PANEL_2CTA"); two_ok = (e && e[0] == '0') ? 0 : 1; }
-    if (two_ok && p.skip_bulk && !p.fast && p.perm == nullptr) {
-        GQ_CHECK_CUDA(cudaFuncSetAttribute(gptq_layer_kernel<QT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_NO_PERM));
-        gptq_layer_kernel<QT, 2><<<grid, NT, SMEM_NO_PERM, st>>>(p);
-        gq_count_launches(1);
-        GQ_CHECK_CUDA(cudaGetLastError());
-        return GQ_OK;
-    }
     const size_t smem = p.perm == nullptr ? SMEM_NO_PERM : sizeof(Smem);
-    GQ_CHECK_CUDA(cudaFuncSetAttribute(gptq_layer_kernel<QT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-    gptq_layer_kernel<QT, 1><<<grid, NT, smem, st>>>(p);
+    GQ_CHECK_CUDA(cudaFuncSetAttribute(gptq_layer_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    gptq_layer_kernel<QT><<<grid, NT, smem, st>>>(p);
     gq_count_launches(1);
     GQ_CHECK_CUDA(cudaGetLastError());
     return GQ_OK;

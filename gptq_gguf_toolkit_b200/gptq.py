@@ -87,7 +87,8 @@ class GPTQ:
         self.static_groups = static_groups
         self.grid = grid
         self.rmin, self.rdelta, self.nstep = rmin, rdelta, nstep
-        self.mode = {"exact": L.GQ_MODE_EXACT, "fast": L.GQ_MODE_FAST}[mode]
+        self.mode = {"exact": L.GQ_MODE_EXACT, "fast": L.GQ_MODE_FAST, "exact_left": L.GQ_MODE_EXACT_LEFT,
+                     "exact_right": L.GQ_MODE_EXACT_RIGHT}[mode]
         self.W_device, self.W_dtype, self.W_shape = self.W.device, self.W.dtype, self.W.shape
         self.hessian = hessian if hessian is not None else HessianAccumulator(self.d_col)
         self.hessian.users += 1

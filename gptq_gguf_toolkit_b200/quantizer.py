@@ -439,7 +439,7 @@ class Quantizer:
         kw = self.quantizer_kwargs
         args = dict(block_size=kw.get("block_size", 128) or W.shape[1], rmin=kw.get("rmin", -1.0),
                     rdelta=kw.get("rdelta", 0.1), nstep=kw.get("nstep", 20), packed=True, wdeq_dtype=dtype,
-                    mode={"exact": 0, "fast": 1}[kw.get("mode", "exact")], static_groups=static_groups, perm=perm)
+                    mode={"exact": 0, "fast": 1, "exact_left": 2, "exact_right": 3}[kw.get("mode", "exact")], static_groups=static_groups, perm=perm)
         if world == 1:
             return ops.gptq_quantize(W, U, qt, stream=stream, **args)[:7]
         # Row slice of this rank (in units of the kernel's 32-row CTA tile), then one all-gather per result tensor.
