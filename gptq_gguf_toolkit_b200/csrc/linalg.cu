@@ -267,15 +267,20 @@ __global__ void __launch_bounds__(DT2) chol_diag_v2_kernel(float *A, float *Binv
         }
         __syncthreads();
         // ---- (b) rank-32 updates with the finished panel (4 x 4 register tiles) ----
+        // A tile takes every nt-th row (and, for L, every nt-th column) of the trailing part, so that the lanes of a warp
+        // (consecutive tc) read CONSECUTIVE rows with LDS.128: the row stride of 132 floats spreads eight consecutive rows
+        // over all 32 banks.  (Blocked 4 x 4 tiles put the lanes 4 rows = 16 banks apart: a 16-way conflict on every load.)
+        // L tiles near the diagonal also produce entries above it; the upper part of L is scratch and never read.
         const int lo = base + PW, R = NB - lo;
         if (R > 0) {
             const int nt = R / 4, nLt = nt * nt, nXc = lo / 4, nXt = nt * nXc;
             for (int t = tid; t < nLt + nXt; t += DT2) {
                 const bool isX = t >= nLt;
                 int ti, tc;
-                if (!isX) { ti = t / nt; tc = t - ti * nt; if (tc > ti) continue; }
+                if (!isX) { ti = t / nt; tc = t - ti * nt; }
                 else { const int u = t - nLt; ti = u / nXc; tc = u - ti * nXc; }
-                const int i0 = lo + 4 * ti, c0 = isX ? 4 * tc : lo + 4 * tc;
+                const int i0 = lo + ti;                       // rows i0 + nt * r
+                const int c0 = isX ? 4 * tc : lo + tc;        // X: columns c0 .. c0+3;  L: columns c0 + nt * q
                 float acc[4][4];
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
@@ -285,10 +290,10 @@ __global__ void __launch_bounds__(DT2) chol_diag_v2_kernel(float *A, float *Binv
                 for (int k = base; k < lo; k += 4) {
                     float4 a[4], b[4];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4 *>(&s.L[(i0 + r) * LS + k]);
-                    if (!isX) {      // b[q] = L[c0+q][k..k+3]
+                    for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4 *>(&s.L[(i0 + nt * r) * LS + k]);
+                    if (!isX) {      // b[q] = L[c0 + nt*q][k..k+3]
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const float4 *>(&s.L[(c0 + q) * LS + k]);
+                        for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const float4 *>(&s.L[(c0 + nt * q) * LS + k]);
 #pragma unroll
                         for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -314,12 +319,23 @@ __global__ void __launch_bounds__(DT2) chol_diag_v2_kernel(float *A, float *Binv
                         }
                     }
                 }
-                float *T = isX ? s.X : s.L;
+                if (isX) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    float4 v = *reinterpret_cast<float4 *>(&T[(i0 + r) * LS + c0]);
-                    v.x -= acc[r][0]; v.y -= acc[r][1]; v.z -= acc[r][2]; v.w -= acc[r][3];
-                    *reinterpret_cast<float4 *>(&T[(i0 + r) * LS + c0]) = v;
+                    for (int r = 0; r < 4; ++r) {
+                        float4 v = *reinterpret_cast<float4 *>(&s.X[(i0 + nt * r) * LS + c0]);
+                        v.x -= acc[r][0]; v.y -= acc[r][1]; v.z -= acc[r][2]; v.w -= acc[r][3];
+                        *reinterpret_cast<float4 *>(&s.X[(i0 + nt * r) * LS + c0]) = v;
+                    }
+                } else {
+                    float v[4][4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) v[r][q] = s.L[(i0 + nt * r) * LS + c0 + nt * q];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) s.L[(i0 + nt * r) * LS + c0 + nt * q] = v[r][q] - acc[r][q];
                 }
             }
         }

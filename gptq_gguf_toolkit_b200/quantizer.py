@@ -146,6 +146,8 @@ class Quantizer:
         self.fused_installed: List[str] = []
         self._split_ok: Optional[bool] = None
         self._side_streams: list = []
+        self._gather_stream = None
+        self._gather_stream_used = False
         self._mask_flags: list = []
         self.timer = timer or PhaseTimer(False)
         self.results: Dict[str, Dict[str, Any]] = {}    # module name -> data.pth dict (+ "packed"), if keep_results
@@ -300,17 +302,27 @@ class Quantizer:
         kw = self.quantizer_kwargs
         hs = [handles[n] for n in names]
         acc = hs[0].hessian
-        with self.timer.span("allreduce"):
-            acc.all_reduce()                                               # gptq.py:131-132
         rows = [h.d_row for h in hs]
+        side = self._side_stream(gi) if overlap else None
+        # fp32 working copy of all members, stacked row-wise (gptq.py:138)
+        W = torch.cat([h.layer.weight.data.float() for h in hs], dim=0).contiguous()
+        # With several ranks and a side stream the Hessian all-reduce and the dead-channel fix run on the side stream too
+        # (their only consumer is the Cholesky chain behind them), so that the forward in flight on the main stream -- this
+        # runs inside a hook of the last calibration batch -- is not held up by the collective.
+        pre = side if (side is not None and _dist_on()) else None
+        if pre is not None:
+            pre.wait_stream(torch.cuda.current_stream(W.device))
+        with (torch.cuda.stream(pre) if pre is not None else contextlib.nullcontext()):
+            with self.timer.span("allreduce"):
+                acc.all_reduce()                                               # gptq.py:131-132
+            with self.timer.span("prepare_host"):
+                ops.pre_step(acc.H, W)                                         # gptq.py:134-141
+                if len(hs) > 1:
+                    masks = torch.stack([(w == 0).all(dim=0) for w in W.split(rows, dim=0)])
+                    self._mask_flags.append((names, (masks != masks[0:1]).any()))   # checked at the end (no host sync here)
+        if pre is not None and kw.get("act_order", False):
+            torch.cuda.current_stream(W.device).wait_stream(pre)      # act_order reads diag(H) on the main stream below
         with self.timer.span("prepare_host"):
-            # fp32 working copy of all members, stacked row-wise (gptq.py:138)
-            W = torch.cat([h.layer.weight.data.float() for h in hs], dim=0).contiguous()
-            ops.pre_step(acc.H, W)                                         # gptq.py:134-141
-            if len(hs) > 1:
-                masks = torch.stack([(w == 0).all(dim=0) for w in W.split(rows, dim=0)])
-                self._mask_flags.append((names, (masks != masks[0:1]).any()))   # checked at the end (no host sync here)
-            side = self._side_stream(gi) if overlap else None
             # act_order (gptq.py:209-216): the loop runs on W[:, perm] with the factor of H[perm][:, perm]; Q3_K
             # members ignore it (gptq.py:204-206) and need the plain factor
             q3 = [quant_config.get(n.split(".")[-1], GGMLQuantizationType.Q4_K) == GGMLQuantizationType.Q3_K for n in names]
@@ -369,16 +381,26 @@ class Quantizer:
             for plan in plans:
                 if plan[6] is not None:
                     main.wait_event(plan[6])
+        # With several ranks the all-gathers of a group's results run on a communication stream (_sharded_gptq), so the
+        # next group's column loop does not wait for them: launch everything first, then wait once and finish in order.
+        launched_all = []
         for plan in plans:
             if plan[6] is not None and not staged:
                 main.wait_event(plan[6])
-            self._finish_group(plan, self._launch_group(plan, quant_config, rank, world, None))
+            launched_all.append((plan, self._launch_group(plan, quant_config, rank, world, None)))
+        launched = ready = None
+        if deferred is not None:
+            # the deferred group: column loop on ITS side stream, right behind its Cholesky chain
+            launched = self._launch_group(deferred, quant_config, rank, world, deferred[7])
+            ready = torch.cuda.Event()
+            ready.record(deferred[7])
+        if self._gather_stream_used:
+            main.wait_stream(self._gather_stream)
+            self._gather_stream_used = False
+        for plan, l in launched_all:
+            self._finish_group(plan, l)
         if deferred is None:
             return None
-        # the deferred group: column loop on ITS side stream, right behind its Cholesky chain
-        launched = self._launch_group(deferred, quant_config, rank, world, deferred[7])
-        ready = torch.cuda.Event()
-        ready.record(deferred[7])
 
         def finish():
             main.wait_event(ready)
@@ -454,15 +476,24 @@ class Quantizer:
         Wl[: hi - lo] = W[lo:hi]
         outs = ops.gptq_quantize(Wl, U, qt, stream=stream, **args)[:7]
         full = [torch.empty((world * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for t in outs]
-        if stream is not None:
-            # Wl and the per-rank outputs die when this function returns, long before the side stream has run the kernel
-            # and the all-gathers that use them: tell the caching allocator (otherwise the main stream's next allocations
+        # Stream of the gathers: the deferred group's side stream, else (GPU) a communication stream of this Quantizer, so
+        # that the main stream can go on with the next group's column loop; _quant_group waits for it before the results
+        # are consumed.
+        gstream = stream
+        if gstream is None and W.is_cuda:
+            if self._gather_stream is None:
+                self._gather_stream = torch.cuda.Stream()
+            gstream = self._gather_stream
+            self._gather_stream_used = True
+        if gstream is not None:
+            # Wl and the per-rank outputs die when this function returns, long before the other stream has run the kernel /
+            # the all-gathers that use them: tell the caching allocator (otherwise the main stream's next allocations
             # -- the pass-2 activations -- would reuse the memory underneath the pending kernels).
             for t in (Wl,) + tuple(outs):
                 if t is not None:
-                    t.record_stream(stream)
-            stream.wait_stream(torch.cuda.current_stream(W.device))      # the gather buffers were allocated on the main stream
-        with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
+                    t.record_stream(gstream)
+            gstream.wait_stream(torch.cuda.current_stream(W.device))     # kernel (if on main) done; gather buffers were allocated on main
+        with (torch.cuda.stream(gstream) if gstream is not None else contextlib.nullcontext()):
             with self.timer.span("allgather"):
                 for g, t in zip(full, outs):
                     dist.all_gather_into_tensor(g, t.contiguous())
