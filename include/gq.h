@@ -99,7 +99,8 @@ GQ_API int gq_prepare(float *H, const float *W, int d_row, int d_col, float rel_
                void *workspace, size_t ws_bytes, int *not_pd_flag, gq_stream_t stream);
 
 /* The column-blocked quantise -> error -> rank-k-update loop -- replaces GPTQ.step (gptq.py:146-295)
- * for act_order = static_groups = False (see gq_gptq_quantize_ex for those), one launch per layer.
+ * for act_order = static_groups = False (see gq_gptq_quantize_ex for those); one call per layer (the number of kernel
+ * launches behind it depends on the schedule, see gq_mode).
  *   W     (d_row, d_col) fp32 working copy; CLOBBERED (holds the propagated errors on return).
  *   U     from gq_prepare.
  *   rmin, rdelta, nstep: K-quant search parameters (quant_utils.py:66-68), doubles like Python floats.
