@@ -492,11 +492,8 @@ __global__ void __launch_bounds__(NT, 2) exact_update_kernel(const LayerParams p
 
 int launch_exact_update(const LayerParams &p, int c, cudaStream_t st) {
     const size_t smem = (size_t)S * (US_FLOATS + ES_FLOATS) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        GQ_CHECK_CUDA(cudaFuncSetAttribute(exact_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    // per launch, like launch_layer: the attribute belongs to the current device's context, a process may use several
+    GQ_CHECK_CUDA(cudaFuncSetAttribute(exact_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nwin = (p.d_col - c - GQ_QK_K) / GQ_QK_K;
     if (nwin <= 0) return GQ_OK;
     dim3 grid(nwin, (p.d_row + R - 1) / R);
