@@ -101,6 +101,10 @@ def main():
             for name, mode in (("auto", 0), ("left", 2), ("right", 3)):
                 mn, _ = timed(lambda: ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16, mode=mode), warm=1, it=2)
                 res[name] = mn
+            if "experimental" in what:      # exact_update_v2_kernel (GQ_UPDATE_V2=1, read by the library on every launch)
+                os.environ["GQ_UPDATE_V2"] = "1"
+                res["right+update_v2"], _ = timed(lambda: ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16, mode=3), warm=1, it=2)
+                os.environ["GQ_UPDATE_V2"] = "0"
             print(f"schedules {rows}x{n}: " + ", ".join(f"{k} {v:.2f} ms" for k, v in res.items()), flush=True)
             del U, W0
     if "rtn" in what:
