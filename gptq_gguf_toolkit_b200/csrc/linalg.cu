@@ -10,6 +10,9 @@
 // The triangular inverse is a log-depth pairwise merge  inv([[A,0],[C,B]]) = [[Ai,0],[-Bi C Ai, Bi]],
 // whose work is all GEMM (zero tiles of the triangular factors are skipped).
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <vector>
 
 #include "gemm_tf32.cuh"
 #include "sgemm.cuh"
@@ -438,6 +441,33 @@ extern "C" int gq_pre_step(float *H, float *W, int d_row, int d_col, gq_stream_t
 // workspace: A (n*n) | Linv (n*n) | Linv^T (n*n) | nz (n ints) + flag | 3xTF32 operand splits
 namespace {
 size_t split_ws_bytes(size_t n) { return (size_t)(1.25 * (double)n * (double)n) * sizeof(float) + (n * 512 + 1024) * sizeof(float) + 8192; }
+// EXPERIMENTAL (GQ_PREPARE_LOOKAHEAD=1; off by default, not yet run on hardware -- written at the end of round 1 after the
+// GPU budget was spent).  Look-ahead for the blocked Cholesky at n >= 8192: after the panel solve only the NEXT block column
+// is updated on the chain's stream; the rest of the trailing update goes to an auxiliary stream with its own operand-split
+// workspace and is waited for one step later, so that a step costs diag + panel + one block column instead of
+// diag + panel + the whole trailing update.
+bool prepare_lookahead() {
+    const char *e = getenv("GQ_PREPARE_LOOKAHEAD");
+    return e && e[0] == '1';
+}
+struct LookaheadCtx { cudaStream_t aux = nullptr; std::vector<cudaEvent_t> ev; };
+std::mutex g_la_mutex;
+std::map<cudaStream_t, LookaheadCtx> g_la;      // one auxiliary stream + event pool per calling stream
+LookaheadCtx *lookahead_ctx(cudaStream_t st, size_t n_events) {
+    std::lock_guard<std::mutex> lock(g_la_mutex);
+    LookaheadCtx &c = g_la[st];
+    if (c.aux == nullptr) {
+        int prio = 0;
+        if (cudaStreamGetPriority(st, &prio) != cudaSuccess) prio = 0;
+        if (cudaStreamCreateWithPriority(&c.aux, cudaStreamNonBlocking, prio) != cudaSuccess) return nullptr;
+    }
+    while (c.ev.size() < n_events) {
+        cudaEvent_t e;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        c.ev.push_back(e);
+    }
+    return &c;
+}
 bool prepare_diag_v2() {      // read on every call: tests and micro-benchmarks flip it at run time
     const char *e = getenv("GQ_DIAG_V2");
     return !(e && e[0] == '0');
@@ -451,7 +481,8 @@ bool prepare_use_simt() {
 
 extern "C" size_t gq_prepare_workspace_bytes(int d_col) {
     const size_t n = (size_t)d_col;
-    return 3 * n * n * sizeof(float) + (n + 64) * sizeof(int) + 1024 + split_ws_bytes(n);
+    return 3 * n * n * sizeof(float) + (n + 64) * sizeof(int) + 1024 + split_ws_bytes(n) +
+           (prepare_lookahead() ? split_ws_bytes(n) + 1024 : 0);
 }
 
 extern "C" int gq_prepare(float *H, const float *W, int d_row, int d_col, float rel_damp, float *U_out, void *workspace,
@@ -494,14 +525,26 @@ extern "C" int gq_prepare(float *H, const float *W, int d_row, int d_col, float 
     GQ_CHECK_CUDA(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DiagSmem)));
     GQ_CHECK_CUDA(cudaFuncSetAttribute(chol_diag_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DiagSmem2)));
     const bool diag_v2 = prepare_diag_v2();
-    auto tc_gemm = [&](const float *Ap, const float *Bp, float *Cp, int M, int N, int K, int batch, long ab, long bb, long cb,
-                       float alpha, float beta, int tile_mode, int k_mode, bool same) {
+    auto tc_gemm_on = [&](cudaStream_t stream_, void *ws_, const float *Ap, const float *Bp, float *Cp, int M, int N, int K, int batch,
+                          long ab, long bb, long cb, float alpha, float beta, int tile_mode, int k_mode, bool same) {
         tg::GemmArgs g;
         g.A = Ap; g.lda = ld; g.a_batch = ab; g.B = Bp; g.ldb = ld; g.b_batch = bb; g.C = Cp; g.ldc = ld; g.c_batch = cb;
         g.M = M; g.N = N; g.K = K; g.batch = batch; g.alpha = alpha; g.beta = beta; g.tile_mode = tile_mode; g.k_mode = k_mode;
         g.same_ab = same;
-        return tg::gemm_tf32x3_nt(g, sws, sws_bytes, st);
+        return tg::gemm_tf32x3_nt(g, ws_, sws_bytes, stream_);
     };
+    auto tc_gemm = [&](const float *Ap, const float *Bp, float *Cp, int M, int N, int K, int batch, long ab, long bb, long cb,
+                       float alpha, float beta, int tile_mode, int k_mode, bool same) {
+        return tc_gemm_on(st, sws, Ap, Bp, Cp, M, N, K, batch, ab, bb, cb, alpha, beta, tile_mode, k_mode, same);
+    };
+    // look-ahead (experimental, see prepare_lookahead): auxiliary stream, second split workspace, 2 events per step
+    LookaheadCtx *la = nullptr;
+    void *sws2 = nullptr;
+    if (!simt && n >= 8192 && prepare_lookahead() && ws_bytes >= gq_prepare_workspace_bytes(d_col)) {
+        la = lookahead_ctx(st, 2 * (size_t)(n / NB) + 2);
+        sws2 = (void *)(((uintptr_t)sws + sws_bytes + 1023) & ~(uintptr_t)1023);
+    }
+    int la_prev_b = -1;      // index of the event recorded after the previous step's rest-of-trailing update
     for (int k0 = 0; k0 < n; k0 += NB) {
         if (diag_v2) chol_diag_v2_kernel<<<1, DT2, sizeof(DiagSmem2), st>>>(A, Li, simt ? nullptr : LiT, ld, k0, flag);
         else chol_diag_kernel<<<1, DT, sizeof(DiagSmem), st>>>(A, Li, simt ? nullptr : LiT, ld, k0, flag);
@@ -521,11 +564,33 @@ extern "C" int gq_prepare(float *H, const float *W, int d_row, int d_col, float 
                 // both GEMMs are NT (K-contiguous operands); operands are copied (split) before C is written => in place is safe
                 rc = tc_gemm(P, Lkk_inv, P, rem, NB, NB, 1, 0, 0, 0, 1.0f, 0.0f, tg::TM_FULL, tg::KM_FULL, false);
                 if (rc) return rc;
-                rc = tc_gemm(P, P, T, rem, rem, NB, 1, 0, 0, 0, -1.0f, 1.0f, tg::TM_LOWER, tg::KM_FULL, true);   // T -= P P^T
+                if (la != nullptr && rem > NB) {
+                    const int step = k0 / NB;
+                    cudaEvent_t ev_panel = la->ev[2 * step], ev_b = la->ev[2 * step + 1];
+                    GQ_CHECK_CUDA(cudaEventRecord(ev_panel, st));
+                    GQ_CHECK_CUDA(cudaStreamWaitEvent(la->aux, ev_panel, 0));
+                    // the next block column received the previous step's rest-of-trailing update on the auxiliary stream
+                    if (la_prev_b >= 0) GQ_CHECK_CUDA(cudaStreamWaitEvent(st, la->ev[la_prev_b], 0));
+                    // (A) next block column, on the chain's stream:  T[:, 0:128] -= P * P[0:128]^T
+                    rc = tc_gemm(P, P, T, rem, NB, NB, 1, 0, 0, 0, -1.0f, 1.0f, tg::TM_FULL, tg::KM_FULL, false);
+                    if (rc) return rc;
+                    // (B) the rest, on the auxiliary stream:  T[128:, 128:] -= P[128:] P[128:]^T  (lower tiles)
+                    const float *P2 = P + (size_t)NB * ld;
+                    float *T2 = T + (size_t)NB * ld + NB;
+                    rc = tc_gemm_on(la->aux, sws2, P2, P2, T2, rem - NB, rem - NB, NB, 1, 0, 0, 0, -1.0f, 1.0f, tg::TM_LOWER, tg::KM_FULL, true);
+                    if (rc) return rc;
+                    GQ_CHECK_CUDA(cudaEventRecord(ev_b, la->aux));
+                    la_prev_b = 2 * step + 1;
+                } else {
+                    if (la_prev_b >= 0) { GQ_CHECK_CUDA(cudaStreamWaitEvent(st, la->ev[la_prev_b], 0)); la_prev_b = -1; }
+                    rc = tc_gemm(P, P, T, rem, rem, NB, 1, 0, 0, 0, -1.0f, 1.0f, tg::TM_LOWER, tg::KM_FULL, true);   // T -= P P^T
+                }
             }
             if (rc) return rc;
         }
     }
+
+    if (la_prev_b >= 0) GQ_CHECK_CUDA(cudaStreamWaitEvent(st, la->ev[la_prev_b], 0));    // look-ahead: join the auxiliary stream
 
     // --- X = inv(L) by pairwise merging of diagonal blocks:  X21 = -X22 * L21 * X11.  U_out is the scratch. ---
     // Tensor path keeps Y = X^T as well so that every product is NT:

@@ -68,6 +68,15 @@ def main():
                 mn, av = timed(lambda: ops.prepare(H0.clone(), W, 0.01), warm=1, it=2)
                 print(f"prepare n={n} GQ_DIAG_V2={v}: {mn:.2f} ms (avg {av:.2f}), launches/call {(ops.launch_count() - l0) // 3}", flush=True)
             os.environ["GQ_DIAG_V2"] = "1"
+            if "experimental" in what and n >= 8192:      # look-ahead Cholesky (GQ_PREPARE_LOOKAHEAD=1), checked against the default U
+                Hc = H0.clone(); U_ref, _ = ops.prepare(Hc, W, 0.01)
+                os.environ["GQ_PREPARE_LOOKAHEAD"] = "1"
+                Hc = H0.clone(); U_la, _ = ops.prepare(Hc, W, 0.01)
+                torch.cuda.synchronize()
+                print(f"prepare n={n} look-ahead: max |U - U_default| / max|U| = {float((U_la - U_ref).abs().max() / U_ref.abs().max()):.2e}", flush=True)
+                mn, av = timed(lambda: ops.prepare(H0.clone(), W, 0.01), warm=1, it=2)
+                print(f"prepare n={n} GQ_PREPARE_LOOKAHEAD=1: {mn:.2f} ms (avg {av:.2f})", flush=True)
+                os.environ["GQ_PREPARE_LOOKAHEAD"] = "0"
     if "hessian" in what:
         for n, T in ((4096, 16384), (14336, 16384)):
             X = torch.randn(T, n, device="cuda").to(torch.bfloat16)

@@ -3,7 +3,8 @@
 GQ_MODE_EXACT_LEFT  = one left-looking launch per layer (every 32-row CTA applies all earlier blocks to its own tile);
 GQ_MODE_EXACT_RIGHT = per 256-column super-block a panel launch + exact_update_kernel over the whole trailing part
                       (used for row slices of wide projections on several GPUs, where the left-looking kernel leaves
-                      most SMs idle);  GQ_MODE_EXACT picks one of them by a cost model.
+                      most SMs idle);  GQ_MODE_EXACT picks right-looking from 4 super-blocks up (measured faster at
+                      every Llama-3-8B shape), left-looking for narrower layers.
 Both must reproduce the reference goldens (gptq.py:146-295) and the oracle bit for bit, for all five types, ragged row
 counts, the static_groups / act_order variants, and a d_col = 14336 slice like the one a rank of an 8-GPU run gets."""
 import os
