@@ -358,30 +358,64 @@ def main():
         for k in prof:
             prof[k] = prof[k] / args.steps
 
-    left = None
-    if args.compare_left > 0 and main_mode == "exact":
+    # ---- optional extras.  The headline numbers above are complete at this point; a failure in an extra (they fail the same
+    # way on every rank: same code, same shapes) is recorded in "notes" instead of losing the whole JSON line.
+    notes = []
+
+    def guarded(what, fn):
+        try:
+            return fn()
+        except Exception as ex:  # noqa: BLE001
+            notes.append(f"{what} failed: {type(ex).__name__}: {str(ex)[:200]}")
+            return None
+
+    def run_left():
         one_step(False, "exact_left")
         lt = [one_step(False, "exact_left") for _ in range(args.compare_left)]
-        left = {"value": sum(t[0] for t in lt) / len(lt), "unit": "s", "steps": args.compare_left,
+        return {"value": sum(t[0] for t in lt) / len(lt), "unit": "s", "steps": args.compare_left,
                 "phases_s": {k: round(v, 4) for k, v in sorted(lt[-1][1].items())},
                 "note": "GQ_MODE_EXACT_LEFT: one left-looking launch per layer; bit-identical outputs"}
 
-    fast = None
-    if args.mode == "both":
+    def run_fast():
         # one extra step with the tcgen05 rank-k path; CUDA events around every rank-k GEMM launch (gq_profile_*)
         one_step(False, "fast")
         ops.profile_enable(True)
-        secs_f, ph_f, _, _, _, _ = one_step(False, "fast")
-        pr = ops.profile_read()
-        ops.profile_enable(False)
-        fast = (secs_f, ph_f, pr)
+        try:
+            secs_f, ph_f, _, _, _, _ = one_step(False, "fast")
+            pr = ops.profile_read()
+        finally:
+            ops.profile_enable(False)
+        return (secs_f, ph_f, pr)
 
-    e2e = None
-    if not args.no_e2e:
-        host_w = {n: t.to("cpu").pin_memory() for n, t in pristine.items()}
+    def run_e2e():
+        nonlocal host_w
+        # pinned host copies of the pristine weights (16 GB per rank for Llama-3-8B); every rank must succeed, otherwise all
+        # ranks skip the end-to-end step together (a rank that bails out alone would leave the others in a collective)
+        ok, why = 1, ""
+        try:
+            host_w = {}
+            for n, t in pristine.items():
+                buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                buf.copy_(t)
+                host_w[n] = buf
+            torch.cuda.synchronize()
+        except Exception as ex:  # noqa: BLE001
+            ok, why, host_w = 0, f"pinned host allocation failed: {type(ex).__name__}", None
+        if world > 1:
+            t = torch.tensor([ok], device=device, dtype=torch.int32)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if ok and int(t.item()) == 0:
+                why = "pinned host allocation failed on another rank"
+            ok = int(t.item())
+        if not ok:
+            return {"value": None, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "unavailable": why}
         one_step(True)      # warm-up: fills torch's pinned-host cache with the result buffers (cudaHostAlloc is slow)
         secs, _, _, h2d, d2h, _ = one_step(True)
-        e2e = {"value": secs, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": 1}
+        return {"value": secs, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": 1}
+
+    left = guarded("left-looking ablation", run_left) if (args.compare_left > 0 and main_mode == "exact") else None
+    fast = guarded("fast mode", run_fast) if args.mode == "both" else None
+    e2e = guarded("e2e", run_e2e) if not args.no_e2e else None
 
     if rank == 0:
         pk = peaks()
@@ -458,16 +492,25 @@ def main():
             }
         if e2e is not None:
             line["e2e"] = e2e
+
+        cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, detail = cpu_reference_sample(w, threads)
+            cpu = guarded("cpu_baseline", lambda: cpu_reference_sample(w, threads))
+        if cpu is not None:
+            v, detail = cpu
             line["cpu_baseline"] = {"value": v, "unit": "s", "cores": threads, "kind": "port",
                                     "sample": "hot path only (Hessian + Cholesky chain + column loop), per-phase bounded samples scaled by "
                                               "algorithmic work to the whole model; see bench.py cpu_reference_sample", "detail": detail}
-        print(json.dumps(line))
+        if notes:
+            line["notes"] = notes
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 if __name__ == "__main__":
