@@ -1,0 +1,100 @@
+"""Host driver on other decoder families that share the reference's module layout (run_quant.sh: model.embed_tokens /
+model.layers / lm_head and the (q|k|v|o|gate|up|down)_proj regex): Mistral and Qwen2 (q/k/v biases), tiny random-init
+models, CPU oracle behind the host logic.  Checked: every projection is quantised once, q/k/v and gate/up still share
+one Hessian each (4 accumulators per block, not 7), the layer weights left in the model are the dequantisation of the emitted
+tensors (quantizer.py:257-264), biases are untouched, and the per-layer result equals a stand-alone GPTQ handle fed with
+the same layer inputs (the reference's protocol, quantizer.py:227-240)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+
+REGEX = r".*layers.*((q|k|v|o|gate|up|down)_proj)$"
+
+
+def _build(family):
+    import transformers
+    torch.manual_seed(0)
+    common = dict(vocab_size=512, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                  num_key_value_heads=2, max_position_embeddings=128, tie_word_embeddings=False)
+    if family == "mistral":
+        cfg = transformers.MistralConfig(**common, sliding_window=None)
+        return transformers.MistralForCausalLM(cfg).float().eval()
+    cfg = transformers.Qwen2Config(**common)
+    return transformers.Qwen2ForCausalLM(cfg).float().eval()
+
+
+@pytest.mark.parametrize("family", ["mistral", "qwen2"])
+def test_driver_on_other_families(monkeypatch, family):
+    from tests import _oracle_backend as ob
+    ob.install(monkeypatch)
+    from gptq_gguf_toolkit_b200 import gptq as G
+    from gptq_gguf_toolkit_b200.quant import build_quant_config
+    from gptq_gguf_toolkit_b200.quantizer import Quantizer
+
+    model = _build(family)
+    pristine = {n: p.data.clone() for n, p in model.named_parameters()}
+    g = torch.Generator().manual_seed(1)
+    loader = [([], {"input_ids": torch.randint(0, 512, (1, 64), generator=g)}) for _ in range(4)]
+
+    made = []
+    orig_init = G.HessianAccumulator.__init__
+
+    def counting_init(self, d_col):
+        orig_init(self, d_col)
+        made.append(self)
+    monkeypatch.setattr(G.HessianAccumulator, "__init__", counting_init)
+    updated = set()
+    orig_update = G.HessianAccumulator.update
+
+    def counting_update(self, x):
+        updated.add(id(self))
+        return orig_update(self, x)
+    monkeypatch.setattr(G.HessianAccumulator, "update", counting_update)
+
+    # capture block 0's layer inputs of the pristine model for the stand-alone handle below
+    seen = {}
+    hooks = [m.register_forward_pre_hook(lambda mod, a, n=n: seen.setdefault(n, []).append(a[0].detach().clone()))
+             for n, m in model.named_modules() if n in ("model.layers.0.self_attn.o_proj", "model.layers.0.mlp.down_proj")]
+    with torch.no_grad():
+        for _, kw in loader:
+            model(**kw)
+    for h in hooks:
+        h.remove()
+
+    q = Quantizer(model, data_loader=loader, quantizable_modules=REGEX,
+                  quantizer_kwargs=dict(rel_damp=0.01, block_size=128, act_order=False, quant_scale="absmax",
+                                        static_groups=False, rmin=-1.0, rdelta=0.1, nstep=20, verbose=False),
+                  pre_block_modules=["model.embed_tokens"], block_modules="model.layers", post_block_modules=["lm_head"],
+                  quant_non_block_modules=True, device="cpu", save_dir=None, keep_results=True, calibration_batch_size=1)
+    q.quantize(build_quant_config("Q4_K", None))
+
+    assert len(q.results) == 2 * 7 + 2
+    # 7 handles per block are created; q/k/v and gate/up are then attached to ONE accumulator each: 4 Hessians per block
+    # receive updates after the first forward has shown which layers share an input (7 in the very first forward of a block
+    # is also fine: sharing is discovered during it)
+    assert len(made) == 2 * 7
+    n_updated = len(updated & {id(a) for a in made})
+    assert n_updated == 2 * 4, n_updated
+    for n, d in q.results.items():
+        w = model.get_submodule(n).weight.data.numpy()
+        deq = orc.dequantize(int(d["q_type"]), d["qweight"].numpy(), d["super_group_scale"].numpy(), d["group_scale_quant"].numpy(),
+                             d["super_group_zero"].numpy(), d["group_zero_quant"].numpy())
+        assert np.array_equal(deq, w), n
+    for n, p in model.named_parameters():
+        if n.endswith(".bias") or "norm" in n:
+            assert torch.equal(p.data, pristine[n]), f"{n} must not change"
+    if family == "qwen2":
+        assert any(n.endswith("q_proj.bias") for n in pristine), "Qwen2 has q/k/v biases"
+
+    # stand-alone handle on block 0's o_proj / down_proj with the inputs the pristine model produced: same result as the
+    # driver (block 0 sees un-quantised inputs in pass 1)
+    for name in ("model.layers.0.self_attn.o_proj", "model.layers.0.mlp.down_proj"):
+        layer = torch.nn.Linear(pristine[name + ".weight"].shape[1], pristine[name + ".weight"].shape[0], bias=False)
+        layer.weight.data = pristine[name + ".weight"].clone()
+        h = G.GPTQ(layer, rel_damp=0.01, block_size=128)
+        for x in seen[name]:
+            h.update(x)
+        five = h.quantize(12)
+        assert torch.equal(five[0], q.results[name]["qweight"]), name
