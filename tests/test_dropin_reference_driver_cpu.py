@@ -1,0 +1,80 @@
+"""The one-line swap of INTEGRATION.md section 1, executed: the UNMODIFIED reference driver
+(quant/gptq/src/quantizer.py::Quantizer -- its hooks, its _quant_group, its dequantize_linear_weight, its data.pth writer)
+with `src.quantizer.GPTQ` replaced by this repo's GPTQ handle class (kernels = the CPU oracle here; libgq on a GPU box).
+
+Needs /root/reference, i.e. runs in the build container only (skipped elsewhere).  Checked on BASELINE configs[0]:
+  * the reference driver runs to completion on our handle and writes its 16 data.pth files with its own schema;
+  * the result is BIT-IDENTICAL to this repo's own driver fed the same way (one sequence per forward) -- the two drivers are
+    interchangeable around the handle;
+  * against the reference's own handle (tests/golden/driver_tiny.npz) it agrees at the statistical boundary B3."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+REF = "/root/reference/quant/gptq"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference checkout (build container only)")
+
+from tests.test_driver_golden_cpu import CFG, KEYS, REGEX  # noqa: E402
+
+
+def _model_and_loader():
+    from transformers import LlamaConfig, LlamaForCausalLM
+    torch.manual_seed(0)
+    model = LlamaForCausalLM(LlamaConfig(**CFG)).float().eval()
+    g = torch.Generator().manual_seed(1)
+    loader = [([], {"input_ids": torch.randint(0, CFG["vocab_size"], (1, 128), generator=g)}) for _ in range(8)]
+    return model, loader
+
+
+KW = dict(rel_damp=0.01, block_size=128, act_order=False, quant_scale="absmax", static_groups=False, rmin=-1.0, rdelta=0.1,
+          nstep=20, verbose=False)
+
+
+def test_reference_driver_runs_on_our_handle(monkeypatch, tmp_path, golden_dir):
+    from tests import _oracle_backend as ob
+    ob.install(monkeypatch)
+    from gptq_gguf_toolkit_b200.gptq import GPTQ as OurGPTQ
+    from gptq_gguf_toolkit_b200.quantizer import Quantizer as OurQuantizer
+    monkeypatch.syspath_prepend(REF)
+    import src.quantizer as refq
+    from src.quant_utils import GGMLQuantizationType as RT
+
+    monkeypatch.setattr(refq, "GPTQ", OurGPTQ)                      # <- the one-line swap
+    model, loader = _model_and_loader()
+    names = ("q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj", "embed_tokens", "lm_head")
+    q = refq.Quantizer(model, data_loader=loader, quantizable_modules=REGEX, quantizer_kwargs=dict(KW),
+                       pre_block_modules=["model.embed_tokens"], post_block_modules=["lm_head"], block_modules="model.layers",
+                       save_dir=str(tmp_path / "ref_driver"), quant_non_block_modules=True, device=torch.device("cpu"))
+    q.quantize({k: RT.Q4_K for k in names})
+    mods = sorted(os.listdir(tmp_path / "ref_driver"))
+    assert len(mods) == 2 * 7 + 2
+    got = {n: torch.load(tmp_path / "ref_driver" / n / "data.pth") for n in mods}
+
+    # (1) this repo's driver, fed one sequence per forward like the reference's loop: bit-identical
+    from gptq_gguf_toolkit_b200.quant_utils import GGMLQuantizationType as OT
+    model2, loader2 = _model_and_loader()
+    ours = OurQuantizer(model2, data_loader=loader2, quantizable_modules=REGEX, quantizer_kwargs=dict(KW),
+                        pre_block_modules=["model.embed_tokens"], post_block_modules=["lm_head"], block_modules="model.layers",
+                        save_dir=None, quant_non_block_modules=True, device="cpu", keep_results=True, calibration_batch_size=1)
+    ours.quantize({k: OT.Q4_K for k in names})
+    for n in mods:
+        if "layers" not in n:
+            continue      # embed / lm_head go through the reference's own RTN code in the reference driver
+        for k in ("qweight", "super_group_scale", "group_scale_quant", "super_group_zero", "group_zero_quant"):
+            assert torch.equal(got[n][k], ours.results[n][k]), f"{n}.{k}: reference driver + our handle != our driver"
+    for (n1, p1), (n2, p2) in zip(model.named_parameters(), model2.named_parameters()):
+        if "layers" in n1:
+            assert torch.equal(p1, p2), n1
+
+    # (2) against the reference's own handle: statistical
+    g = np.load(os.path.join(golden_dir, "driver_tiny.npz"))
+    for n in mods:
+        same = float((got[n]["qweight"].numpy() == g[f"{n}|qweight"]).mean())
+        assert same >= (0.98 if ".layers.0." in n or "layers" not in n else 0.75), (n, same)
+    for n in ("model.embed_tokens", "lm_head"):
+        for k in KEYS:
+            a = got[n][k].numpy()
+            assert np.array_equal(a.view(np.uint16) if a.dtype == np.float16 else a, g[f"{n}|{k}"]), (n, k)
