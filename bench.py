@@ -414,8 +414,10 @@ def main():
         return {"value": secs, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": 1}
 
     left = guarded("left-looking ablation", run_left) if (args.compare_left > 0 and main_mode == "exact") else None
-    fast = guarded("fast mode", run_fast) if args.mode == "both" else None
+    # e2e (a contract key) first; the fast-mode extra only on one GPU: it is an extra of the N = 1 line, and a rank-local
+    # failure in an extra step at N > 1 would leave the other ranks waiting in a collective
     e2e = guarded("e2e", run_e2e) if not args.no_e2e else None
+    fast = guarded("fast mode", run_fast) if (args.mode == "both" and world == 1) else None
 
     if rank == 0:
         pk = peaks()
