@@ -50,6 +50,10 @@ WORKLOADS = {
     "llama3-8b-dev": dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=2, num_attention_heads=32,
                           num_key_value_heads=8, vocab_size=128256, max_position_embeddings=8192, n_seq=32, seq_len=2048,
                           dtype="bfloat16"),
+    # profiling only: ONE block (about 2300 kernel launches per step; an ncu launch list costs ~0.17 s per launch)
+    "llama3-8b-dev1": dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=1, num_attention_heads=32,
+                           num_key_value_heads=8, vocab_size=128256, max_position_embeddings=8192, n_seq=16, seq_len=2048,
+                           dtype="bfloat16"),
     # BASELINE.json configs[0] (plumbing)
     "tiny": dict(hidden_size=256, intermediate_size=768, num_hidden_layers=2, num_attention_heads=4,
                  num_key_value_heads=2, vocab_size=1024, max_position_embeddings=256, n_seq=8, seq_len=128,
