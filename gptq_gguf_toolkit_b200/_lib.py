@@ -43,6 +43,7 @@ SIGNATURES = {
     "gq_profile_enable": (None, [_i]),
     "gq_profile_read": (_i, [C.POINTER(_f), C.POINTER(_i)]),
     "gq_rtn_quantize": (_i, [_vp, _i, _i, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "gq_rtn_quantize_native": (_i, [_vp, _i, _i, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "gq_get_scale_and_zero": (_i, [_vp, _l, _i, _i, _d, _d, _i, _vp, _vp, _l, _vp, _vp, _l, _vp, _vp]),
     "gq_dequantize": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp]),
     "gq_pack": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),

@@ -5,6 +5,7 @@
 //   gq_pack                (replaces pack_Q2K..pack_Q6K, packing_utils.py:33-326)
 // One CTA handles a (32 rows x 256 columns) super-block tile; the grid covers (row tiles, super-blocks), so
 // embed_tokens / lm_head (128256 x 4096) launch 4008 x 16 independent CTAs -- purely HBM/ALU work, no GEMM.
+#include "kquant_bf16.cuh"
 #include "tile.cuh"
 
 namespace {
@@ -102,6 +103,82 @@ template <int QT> int launch_rtn(const RtnParams &p, cudaStream_t st) {
     return GQ_OK;
 }
 
+// EXPERIMENTAL twin of rtn_kernel for BF16 weights with the reference's bf16-arithmetic scale search (kquant_bf16.cuh);
+// everything after the search -- quantize() in fp32, codes, GGUF bytes, dequantised weights -- is the same code.
+// Reached only through gq_rtn_quantize_native; gq_rtn_quantize (fp32 search on widened weights) is untouched.
+template <int QT>
+__global__ void __launch_bounds__(NT) rtn_bf16_kernel(const RtnParams p) {
+    __shared__ RtnSmem sm;
+    constexpr int GS = Fmt<QT>::GS, GPR = GQ_QK_K / GS, V = GS / 4;
+    constexpr int MAXQ = (1 << Fmt<QT>::BITS) - 1;
+    const int tid = threadIdx.x;
+    const int r0 = blockIdx.x * R, sb = blockIdx.y, c = sb * GQ_QK_K;
+    for (int id = tid; id < R * 64; id += NT) {
+        const int row = id >> 6, c4 = id & 63;
+        const long base = (long)min(r0 + row, p.d_row - 1) * p.ld_in + c + 4 * c4;
+        float4 v;
+        v.x = load_as_f32(p.W, base + 0, GQ_BF16); v.y = load_as_f32(p.W, base + 1, GQ_BF16);
+        v.z = load_as_f32(p.W, base + 2, GQ_BF16); v.w = load_as_f32(p.W, base + 3, GQ_BF16);
+        *reinterpret_cast<float4 *>(sm.Wt + wt_idx4(row, c4)) = v;
+    }
+    __syncthreads();
+    for (int task = tid; task < R * GPR; task += NT) {
+        const int row = task / GPR, g = task % GPR;
+        float x[GS];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const float4 t = *reinterpret_cast<const float4 *>(sm.Wt + wt_idx4(row, g * V + v));
+            x[4 * v + 0] = t.x; x[4 * v + 1] = t.y; x[4 * v + 2] = t.z; x[4 * v + 3] = t.w;
+        }
+        float s, z;
+        if constexpr (Fmt<QT>::ASYM) kqb_search_asym<GS, MAXQ>(x, p.sp, s, z);
+        else kqb_search_sym<GS, MAXQ>(x, s, z);
+        sm.gsc[row * 16 + g] = s;
+        sm.gzr[row * 16 + g] = z;
+    }
+    __syncthreads();
+    if (tid < R) {
+        uint16_t db, dmb;
+        kqb_row_finalize<QT>(sm.gsc + tid * 16, sm.gzr + tid * 16, db, dmb, sm.rs.sq[tid], sm.rs.zq[tid]);
+        sm.rs.dbits[tid] = db;
+        sm.rs.dmbits[tid] = dmb;
+        sm.rs.d[tid] = __half2float(__ushort_as_half(db));
+        sm.rs.dm[tid] = __half2float(__ushort_as_half(dmb));
+        if (r0 + tid < p.d_row) {
+            const long gr = r0 + tid;
+            p.d[gr * p.d_stride + sb] = db;
+            p.dmin[gr * p.d_stride + sb] = dmb;
+#pragma unroll
+            for (int g = 0; g < GPR; ++g) {
+                p.sq[gr * p.sq_stride + sb * GPR + g] = sm.rs.sq[tid][g];
+                p.zq[gr * p.sq_stride + sb * GPR + g] = sm.rs.zq[tid][g];
+            }
+        }
+    }
+    __syncthreads();
+    const float lo = (float)Fmt<QT>::QMIN, hi = (float)Fmt<QT>::QMAX;
+    for (int id = tid; id < R * 256; id += NT) {          // quantize() in fp32: quant_utils.py:34-40 promotes bf16 + fp32
+        const int row = id >> 8, col = id & 255, g = col / GS;
+        const float s = __fmul_rn(sm.rs.d[row], kq_code_to_f<QT>(sm.rs.sq[row][g]));
+        const float z = __fmul_rn(sm.rs.dm[row], kq_code_to_f<QT>(sm.rs.zq[row][g]));
+        const int wi = wt_idx(row, col);
+        const float q = kq_quant(sm.Wt[wi], s, z, lo, hi);
+        sm.codes[row * 256 + col] = (uint8_t)(int8_t)(int)q;
+        sm.Wt[wi] = kq_dequant(q, s, z);
+    }
+    __syncthreads();
+    tile_emit<QT, R, NT>(sm.Wt, sm.codes, sm.rs, r0, p.d_row, (size_t)p.nsb * GQ_QK_K, c, sb, p.nsb, p.qweight,
+                         p.packed, p.wdeq, p.wdeq_dtype);
+}
+
+template <int QT> int launch_rtn_bf16(const RtnParams &p, cudaStream_t st) {
+    dim3 grid((p.d_row + R - 1) / R, p.nsb);
+    rtn_bf16_kernel<QT><<<grid, NT, 0, st>>>(p);
+    gq_count_launches(1);
+    GQ_CHECK_CUDA(cudaGetLastError());
+    return GQ_OK;
+}
+
 int dispatch_rtn(int qtype, const RtnParams &p, cudaStream_t st) {
     switch (qtype) {
     case GQ_Q2_K: return launch_rtn<GQ_Q2_K>(p, st);
@@ -178,6 +255,35 @@ extern "C" int gq_rtn_quantize(const void *W, int w_dtype, int d_row, int d_col,
     p.d = d; p.dmin = dmin; p.d_stride = p.nsb; p.sq = (uint8_t *)sq; p.zq = (uint8_t *)zq; p.sq_stride = d_col / f.gs;
     p.qweight = (uint8_t *)qweight; p.packed = packed; p.wdeq = wdeq; p.wdeq_dtype = wdeq_dtype; p.flags = nullptr;
     return dispatch_rtn(qtype, p, (cudaStream_t)stream);
+}
+
+// EXPERIMENTAL (see kquant_bf16.cuh): gq_rtn_quantize for a BF16 weight with the scale search in the reference's bf16
+// arithmetic -- what quantizer.py:278-330 computes for embed_tokens / lm_head of a bf16 model.  Same outputs and conventions.
+extern "C" int gq_rtn_quantize_native(const void *W, int w_dtype, int d_row, int d_col, int qtype, double rmin,
+                                      double rdelta, int nstep, void *qweight, uint16_t *d, void *sq, uint16_t *dmin,
+                                      void *zq, uint8_t *packed, void *wdeq, int wdeq_dtype, gq_stream_t stream) {
+    if (w_dtype != GQ_BF16)      // fp32 weights: the native arithmetic IS the fp32 search; fp16 is not pinned
+        return gq_rtn_quantize(W, w_dtype, d_row, d_col, qtype, rmin, rdelta, nstep, qweight, d, sq, dmin, zq, packed, wdeq,
+                               wdeq_dtype, stream);
+    FmtInfo f;
+    GQ_REQUIRE(gq_fmt_info(qtype, f), "gq_rtn_quantize_native: unknown q_type %d", qtype);
+    GQ_REQUIRE(W && qweight && d && sq && dmin && zq, "gq_rtn_quantize_native: null pointer");
+    GQ_REQUIRE(d_row > 0 && d_col > 0 && d_col % GQ_QK_K == 0, "gq_rtn_quantize_native: d_col=%d must be a positive multiple of 256", d_col);
+    GQ_REQUIRE(nstep >= 0 && nstep < 64, "gq_rtn_quantize_native: nstep=%d out of range [0,63]", nstep);
+    GQ_REQUIRE(((uintptr_t)W | (uintptr_t)qweight | (uintptr_t)wdeq) % 16 == 0, "gq_rtn_quantize_native: W, qweight, wdeq must be 16-byte aligned");
+    RtnParams p;
+    p.W = W; p.w_dtype = w_dtype; p.ld_in = d_col; p.d_row = d_row; p.nsb = d_col / GQ_QK_K;
+    gq_fill_search_params(p.sp, (1 << f.bits) - 1, rmin, rdelta, nstep);
+    p.d = d; p.dmin = dmin; p.d_stride = p.nsb; p.sq = (uint8_t *)sq; p.zq = (uint8_t *)zq; p.sq_stride = d_col / f.gs;
+    p.qweight = (uint8_t *)qweight; p.packed = packed; p.wdeq = wdeq; p.wdeq_dtype = wdeq_dtype; p.flags = nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (qtype) {
+    case GQ_Q2_K: return launch_rtn_bf16<GQ_Q2_K>(p, st);
+    case GQ_Q3_K: return launch_rtn_bf16<GQ_Q3_K>(p, st);
+    case GQ_Q4_K: return launch_rtn_bf16<GQ_Q4_K>(p, st);
+    case GQ_Q5_K: return launch_rtn_bf16<GQ_Q5_K>(p, st);
+    default: return launch_rtn_bf16<GQ_Q6_K>(p, st);
+    }
 }
 
 extern "C" int gq_get_scale_and_zero(const float *x, long x_stride, int rows, int qtype, double rmin, double rdelta,

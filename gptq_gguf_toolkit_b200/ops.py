@@ -187,15 +187,18 @@ def gptq_quantize(W: torch.Tensor, U: torch.Tensor, q_type: int, block_size: int
 
 
 def rtn_quantize(W: torch.Tensor, q_type: int, rmin: float = -1.0, rdelta: float = 0.1, nstep: int = 20,
-                 packed: bool = True, wdeq_dtype: Optional[torch.dtype] = None):
+                 packed: bool = True, wdeq_dtype: Optional[torch.dtype] = None, native_arith: bool = False):
     """RTN K-quant of a weight without Hessian (quantizer.py:278-330).  W is read-only (fp32/fp16/bf16).
-    Returns (qweight, d, sq, dmin, zq, packed|None, wdeq|None)."""
+    Returns (qweight, d, sq, dmin, zq, packed|None, wdeq|None).
+    native_arith (EXPERIMENTAL, see gq_rtn_quantize_native): for a bf16 weight run the scale search in bf16 arithmetic like
+    the reference does; default False = widen to fp32 (the validated path)."""
     L.require_cuda(W)
     assert W.is_contiguous() and W.dim() == 2
     d_row, d_col = W.shape
     qweight, d, sq, dmin, zq, pk, wd = alloc_outputs(q_type, d_row, d_col, W.device, packed, wdeq_dtype)
     with _span("rtn"):
-        L.check(L.load().gq_rtn_quantize(
+        fn = L.load().gq_rtn_quantize_native if native_arith else L.load().gq_rtn_quantize
+        L.check(fn(
             L.ptr(W), L.dtype_code(W.dtype), d_row, d_col, int(q_type), float(rmin), float(rdelta), int(nstep),
             L.ptr(qweight), L.ptr(d), L.ptr(sq), L.ptr(dmin), L.ptr(zq), L.ptr(pk), L.ptr(wd),
             L.dtype_code(wdeq_dtype) if wdeq_dtype is not None else 0, L.stream_of(W.device)))

@@ -153,6 +153,15 @@ GQ_API int gq_rtn_quantize(const void *W, int w_dtype, int d_row, int d_col, int
                     void *qweight, uint16_t *d, void *sq, uint16_t *dmin, void *zq,
                     uint8_t *packed, void *wdeq, int wdeq_dtype, gq_stream_t stream);
 
+/* EXPERIMENTAL (not yet validated on hardware; the CPU oracle's twin is pinned to the reference, tests/golden/rtn_bf16.npz):
+ * gq_rtn_quantize with the scale search in the arithmetic of the weight's own dtype, as the reference does it
+ * (quantizer.py:303-305 passes the weight un-widened): for GQ_BF16 every op of the search rounds to bf16; the final quantize()
+ * is fp32 as in the reference.  Other dtypes fall through to gq_rtn_quantize.  Same arguments and outputs. */
+GQ_API int gq_rtn_quantize_native(const void *W, int w_dtype, int d_row, int d_col, int qtype,
+                    double rmin, double rdelta, int nstep,
+                    void *qweight, uint16_t *d, void *sq, uint16_t *dmin, void *zq,
+                    uint8_t *packed, void *wdeq, int wdeq_dtype, gq_stream_t stream);
+
 /* Scale / min search of one super-block column -- replaces quant_utils.Quantizer.get_scale_and_zero
  * (quant_utils.py:90-145).  x: (rows, 256) fp32 with row stride x_stride (elements).
  * d,dmin: one fp16 per row (stride d_stride elements); sq,zq: 256/group_size codes per row

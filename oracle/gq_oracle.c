@@ -75,6 +75,24 @@ static inline float sum8(const float *v, int n) {
 
 static inline float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
+/* bf16-arithmetic mode of the scale search (orc_rtn_quantize_bf16): the reference runs get_scale_and_zero on the weight in
+ * its ORIGINAL dtype (quantizer.py:303-305), so for a bf16 model every torch op of make_k_quants / make_quants /
+ * get_scale_and_zero computes in fp32 and rounds its result to bf16 (round to nearest even), reductions accumulate in fp32 and
+ * round once, and `python_scalar / tensor` is reciprocal(tensor) ROUNDED, then times the fp32 scalar, rounded again.
+ * Pinned op by op and end to end against the reference on CPU (tests/golden/make_golden_rtn_bf16.py): all four scale
+ * tensors bit-identical for the five types.  RB() is the identity in the fp32 mode, i.e. the fp32 contract is untouched.
+ * The switch is a file-scope flag set by the entry point (test infrastructure: not re-entrant). */
+static int g_bf16 = 0;
+static inline float bf16_rne(float x) {
+    uint32_t u; memcpy(&u, &x, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return x;                 /* NaN */
+    u += 0x7fffu + ((u >> 16) & 1u);
+    u &= 0xffff0000u;
+    float r; memcpy(&r, &u, 4); return r;
+}
+static inline float RB(float x) { return g_bf16 ? bf16_rne(x) : x; }
+#define ORC_EPS_T (g_bf16 ? bf16_rne(ORC_EPS) : ORC_EPS)          /* clamp_min(eps) on a tensor of that dtype */
+
 /* ------------------------------------------------------------------------------------------
  * make_k_quants: quant_utils.py:199-274  (Q2_K, Q4_K, Q5_K; asymmetric weighted LSQ search)
  * Operates on all G groups of one get_scale_and_zero call at once because the
@@ -93,10 +111,10 @@ typedef struct {
 
 static void group_weights(const float *x, int n, float *w) {
     float t[32];
-    for (int k = 0; k < n; ++k) t[k] = x[k] * x[k];
-    float sum_x2 = sum8(t, n);                      /* :203 */
-    float av_x = sqrtf(sum_x2 / (float)n);          /* :204 (IEEE sqrt) */
-    for (int k = 0; k < n; ++k) w[k] = av_x + fabsf(x[k]); /* :205 */
+    for (int k = 0; k < n; ++k) t[k] = RB(x[k] * x[k]);
+    float sum_x2 = RB(sum8(t, n));                  /* :203 */
+    float av_x = RB(sqrtf(RB(sum_x2 / (float)n)));  /* :204 (IEEE sqrt) */
+    for (int k = 0; k < n; ++k) w[k] = RB(av_x + fabsf(x[k])); /* :205 */
 }
 
 static void make_k_quants_call(const float *x, long row_stride, int rows, int n, int maxq,
@@ -117,19 +135,19 @@ static void make_k_quants_call(const float *x, long row_stride, int rows, int n,
         for (int k = 1; k < n; ++k) { mn = fminf(mn, xg[k]); mx = fmaxf(mx, xg[k]); }
         mn = fminf(mn, 0.0f);                        /* :210 */
         s->isconst = (mx == mn);                     /* :211 */
-        s->sum_w = sum8(w, n);                       /* :214 */
-        for (int k = 0; k < n; ++k) t[k] = w[k] * xg[k];
-        s->sum_x = sum8(t, n);                       /* :215 */
-        float scale = (mx - mn) / fmaxq;             /* :218 */
+        s->sum_w = RB(sum8(w, n));                   /* :214 */
+        for (int k = 0; k < n; ++k) t[k] = RB(w[k] * xg[k]);
+        s->sum_x = RB(sum8(t, n));                   /* :215 */
+        float scale = RB(RB(mx - mn) / fmaxq);       /* :218 */
         if (s->isconst) scale = 0.0f;                /* :219 */
-        float iscale = 1.0f / fmaxf(scale, ORC_EPS); /* :220 */
+        float iscale = RB(1.0f / fmaxf(scale, ORC_EPS_T)); /* :220 */
         for (int k = 0; k < n; ++k) {
-            float q = clampf(rintf((xg[k] - mn) * iscale), 0.0f, fmaxq); /* :223 */
+            float q = clampf(rintf(RB(RB(xg[k] - mn) * iscale)), 0.0f, fmaxq); /* :223 */
             if (s->isconst) q = 0.0f;                /* :225 */
-            float diff = (scale * q + mn) - xg[k];   /* :230 */
-            t[k] = w[k] * (diff * diff);             /* :231-232 */
+            float diff = RB(RB(RB(scale * q) + mn) - xg[k]);   /* :230 */
+            t[k] = RB(w[k] * RB(diff * diff));       /* :231-232 */
         }
-        s->best_err = sum8(t, n);
+        s->best_err = RB(sum8(t, n));
         s->xmin = mn; s->xmax = mx; s->best_scale = scale;
     }
 
@@ -145,17 +163,17 @@ static void make_k_quants_call(const float *x, long row_stride, int rows, int n,
                 float w[32], a[32], b[32], c[32];
                 group_weights(xg, n, w);
                 /* :241  scalar / tensor  ==  reciprocal(tensor) * scalar */
-                float is = (1.0f / fmaxf(s->xmax - s->xmin, ORC_EPS)) * num;
+                float is = RB(RB(1.0f / fmaxf(RB(s->xmax - s->xmin), ORC_EPS_T)) * num);
                 for (int k = 0; k < n; ++k) {
-                    float qf = clampf(rintf((xg[k] - s->xmin) * is), 0.0f, fmaxq); /* :242 */
+                    float qf = clampf(rintf(RB(RB(xg[k] - s->xmin) * is)), 0.0f, fmaxq); /* :242 */
                     uint8_t L = s->isconst ? 0 : (uint8_t)qf;                      /* :243 */
                     uint8_t L2 = (uint8_t)(L * L);      /* :246 uint8 ** 2 wraps */
-                    a[k] = w[k] * (float)L;             /* :245 */
-                    b[k] = w[k] * (float)L2;            /* :246 */
-                    c[k] = (w[k] * xg[k]) * (float)L;   /* :247 */
+                    a[k] = RB(w[k] * (float)L);             /* :245 */
+                    b[k] = RB(w[k] * (float)L2);            /* :246 */
+                    c[k] = RB(RB(w[k] * xg[k]) * (float)L); /* :247 */
                 }
-                s->s_l = sum8(a, n); s->s_l2 = sum8(b, n); s->s_xl = sum8(c, n);
-                float D = s->sum_w * s->s_l2 - s->s_l * s->s_l;   /* :249 */
+                s->s_l = RB(sum8(a, n)); s->s_l2 = RB(sum8(b, n)); s->s_xl = RB(sum8(c, n));
+                float D = RB(RB(s->sum_w * s->s_l2) - RB(s->s_l * s->s_l));   /* :249 */
                 if (D > ORC_EPS) any_valid |= 1;                   /* :250 */
             }
             if (!any_valid) continue;                              /* :251-252 */
@@ -167,21 +185,21 @@ static void make_k_quants_call(const float *x, long row_stride, int rows, int n,
                 kq_state_t *s = &st[g];
                 float w[32], t[32];
                 group_weights(xg, n, w);
-                float is = (1.0f / fmaxf(s->xmax - s->xmin, ORC_EPS)) * num;
-                float D = s->sum_w * s->s_l2 - s->s_l * s->s_l;
-                float sc = (s->sum_w * s->s_xl - s->sum_x * s->s_l) / D;  /* :254 */
-                float mn = (s->s_l2 * s->sum_x - s->s_l * s->s_xl) / D;   /* :255 */
+                float is = RB(RB(1.0f / fmaxf(RB(s->xmax - s->xmin), ORC_EPS_T)) * num);
+                float D = RB(RB(s->sum_w * s->s_l2) - RB(s->s_l * s->s_l));
+                float sc = RB(RB(RB(s->sum_w * s->s_xl) - RB(s->sum_x * s->s_l)) / D);  /* :254 */
+                float mn = RB(RB(RB(s->s_l2 * s->sum_x) - RB(s->s_l * s->s_xl)) / D);   /* :255 */
                 if (mn > 0.0f) {                                           /* :257-260 */
-                    sc = s->s_xl / fmaxf(s->s_l2, ORC_EPS);
+                    sc = RB(s->s_xl / fmaxf(s->s_l2, ORC_EPS_T));
                     mn = 0.0f;
                 }
                 for (int k = 0; k < n; ++k) {
-                    float qf = clampf(rintf((xg[k] - s->xmin) * is), 0.0f, fmaxq);
+                    float qf = clampf(rintf(RB(RB(xg[k] - s->xmin) * is)), 0.0f, fmaxq);
                     uint8_t L = s->isconst ? 0 : (uint8_t)qf;
-                    float diff = (sc * (float)L + mn) - xg[k];             /* :262 */
-                    t[k] = w[k] * (diff * diff);                           /* :263-264 */
+                    float diff = RB(RB(RB(sc * (float)L) + mn) - xg[k]);   /* :262 */
+                    t[k] = RB(w[k] * RB(diff * diff));                     /* :263-264 */
                 }
-                float cand = sum8(t, n);
+                float cand = RB(sum8(t, n));
                 if (cand < s->best_err) {                                  /* :266-270 */
                     s->best_err = cand; s->best_scale = sc; s->xmin = mn;  /* xmin IS best_min */
                     any_acc |= 1;
@@ -210,7 +228,7 @@ static void make_quants_call(const float *x, long row_stride, int rows, int n, i
         mx = fmaxf(fabsf(mn), mx);                   /* :153 */
         if (mn < 0.0f) mn = -mx;                     /* :154-156 */
         if (mn == mx) { mn = -1.0f; mx = 1.0f; }     /* :157-159 */
-        scale_out[g] = (mx - mn) / (float)maxq;      /* :161 */
+        scale_out[g] = RB(RB(mx - mn) / (float)maxq);      /* :161 */
         zero_out[g] = 0.0f;                          /* :195 */
     }
 }
@@ -244,13 +262,13 @@ int orc_get_scale_and_zero(const float *x, long row_stride, int rows, int qtype,
         const float *s = gs + (long)r * gpr, *z = gz + (long)r * gpr;
         float ms = s[0], mz = z[0];
         for (int g = 1; g < gpr; ++g) { ms = fmaxf(ms, s[g]); mz = fmaxf(mz, z[g]); }  /* :121 */
-        d[r * d_stride] = f2h(ms / smq);                                                 /* :124 */
-        dmin[r * dmin_stride] = f2h(mz / smq);                                           /* :125 */
-        float inv_s = ms > 0.0f ? (1.0f / ms) * smq : 0.0f;                              /* :128 */
-        float inv_z = mz > 0.0f ? (1.0f / mz) * smq : 0.0f;                              /* :129 */
+        d[r * d_stride] = f2h(RB(ms / smq));                                             /* :124 */
+        dmin[r * dmin_stride] = f2h(RB(mz / smq));                                       /* :125 */
+        float inv_s = ms > 0.0f ? RB(RB(1.0f / ms) * smq) : 0.0f;                        /* :128 */
+        float inv_z = mz > 0.0f ? RB(RB(1.0f / mz) * smq) : 0.0f;                        /* :129 */
         for (int g = 0; g < gpr; ++g) {
-            sq[r * sq_stride + g] = (uint8_t)(int)clampf(rintf(inv_s * s[g]), 0.0f, smq); /* :132-137 */
-            zq[r * zq_stride + g] = (uint8_t)(int)clampf(rintf(inv_z * z[g]), 0.0f, smq); /* :138-143 */
+            sq[r * sq_stride + g] = (uint8_t)(int)clampf(rintf(RB(inv_s * s[g])), 0.0f, smq); /* :132-137 */
+            zq[r * zq_stride + g] = (uint8_t)(int)clampf(rintf(RB(inv_z * z[g])), 0.0f, smq); /* :138-143 */
         }
     }
     free(gs); free(gz);
@@ -426,6 +444,17 @@ int orc_rtn_quantize(const float *W, int d_row, int d_col, int qtype,
             qweight[(long)r * d_col + c] = (uint8_t)(int8_t)(int)q;
         }
     return 0;
+}
+
+/* The same for a bf16 weight (values passed widened to fp32): the scale search runs in bf16 arithmetic (see RB above), the
+ * final quantize() in fp32 like the reference's (quant_utils.py:34-40 promotes bf16 + fp32 to fp32). */
+int orc_rtn_quantize_bf16(const float *W, int d_row, int d_col, int qtype,
+                          double rmin, double rdelta, int nstep,
+                          uint8_t *qweight, uint16_t *d, uint16_t *dmin, uint8_t *sq, uint8_t *zq) {
+    g_bf16 = 1;
+    const int rc = orc_rtn_quantize(W, d_row, d_col, qtype, rmin, rdelta, nstep, qweight, d, dmin, sq, zq);
+    g_bf16 = 0;
+    return rc;
 }
 
 /* dequantize_linear_weight: quant_utils.py:277-310 */
