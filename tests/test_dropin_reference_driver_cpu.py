@@ -78,3 +78,40 @@ def test_reference_driver_runs_on_our_handle(monkeypatch, tmp_path, golden_dir):
         for k in KEYS:
             a = got[n][k].numpy()
             assert np.array_equal(a.view(np.uint16) if a.dtype == np.float16 else a, g[f"{n}|{k}"]), (n, k)
+
+
+def test_bf16_model_non_block_modules_match_reference_with_native_arith(monkeypatch):
+    """embed_tokens / lm_head of a BF16 model: with rtn_native_arith=True this repo's driver reproduces the reference's
+    _quant_non_block_module (bf16-arithmetic scale search, quantizer.py:278-330) bit for bit; with the default (weights
+    widened to fp32) it does not -- the documented deviation of DESIGN.md section 2."""
+    from tests import _oracle_backend as ob
+    ob.install(monkeypatch)
+    from gptq_gguf_toolkit_b200.quantizer import Quantizer as OurQuantizer
+    from gptq_gguf_toolkit_b200.quant_utils import GGMLQuantizationType as OT
+    monkeypatch.syspath_prepend(REF)
+    import src.quantizer as refq
+    from src.quant_utils import GGMLQuantizationType as RT
+
+    class _Self:
+        quantizer_kwargs = {}
+
+    def run(native):
+        model, loader = _model_and_loader()
+        model = model.to(torch.bfloat16)
+        pristine = {n: model.get_submodule(n).weight.data.clone() for n in ("model.embed_tokens", "lm_head")}
+        q = OurQuantizer(model, data_loader=loader[:2], quantizable_modules=REGEX, quantizer_kwargs=dict(KW),
+                         pre_block_modules=["model.embed_tokens"], post_block_modules=["lm_head"], block_modules="model.layers",
+                         save_dir=None, quant_non_block_modules=True, device="cpu", keep_results=True, calibration_batch_size=2,
+                         rtn_native_arith=native)
+        q.quantize({k: OT.Q4_K for k in ("q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj",
+                                         "embed_tokens", "lm_head")})
+        return q, pristine
+
+    q_nat, pristine = run(True)
+    q_def, _ = run(False)
+    for n, w in pristine.items():
+        ref = refq.Quantizer._quant_non_block_module(_Self(), w.clone(), RT.Q4_K)
+        names = ("qweight", "super_group_scale", "group_scale_quant", "super_group_zero", "group_zero_quant")
+        for k, r in zip(names, ref):
+            assert torch.equal(q_nat.results[n][k], r), f"{n}.{k}: native bf16 arithmetic must equal the reference"
+        assert not torch.equal(q_def.results[n]["qweight"], ref[0]), "fp32-widened search differs on bf16 weights (documented)"
