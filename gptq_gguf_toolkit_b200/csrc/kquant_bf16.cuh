@@ -10,7 +10,9 @@
 // This header deliberately DUPLICATES the search of kquant.cuh instead of parametrising it: the fp32 path is the validated
 // contract of the GPTQ layers and must not be touched by an unvalidated variant.
 #pragma once
+#ifndef GQ_HOST_SHIM      // tests compile this header for the host through a shim of the intrinsics (tests/helpers/host_shim)
 #include "kquant.cuh"
+#endif
 
 __device__ __forceinline__ float rb16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
