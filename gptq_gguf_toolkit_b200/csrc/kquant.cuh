@@ -4,7 +4,9 @@
 // packing_utils.py of IST-DASLab/gptq-gguf-toolkit); every rounding is spelled out with an _rn
 // intrinsic so that neither -fmad nor instruction selection can change it.
 #pragma once
+#ifndef GQ_HOST_SHIM      // the CPU suite compiles this header for the host through a shim of the intrinsics (tests/helpers/host_shim)
 #include "common.cuh"
+#endif
 
 // torch Tensor.sum(dim=1) over GS in {16,32} contiguous fp32 == 8 lane accumulators
 // lane[l] = ((x[l]+x[l+8])+x[l+16])+x[l+24], folded in order starting from 0.

@@ -1,6 +1,6 @@
-// TEST-ONLY host shim: lets g++ compile gptq_gguf_toolkit_b200/csrc/kquant_bf16.cuh (device code) for the CPU, so that the
-// arithmetic of the experimental bf16 scale search can be checked against the reference golden without a GPU
-// (tests/test_kquant_bf16_source_cpu.py).  It stands in for kquant.cuh / common.cuh with just what that header uses; every CUDA
+// TEST-ONLY host shim: lets g++ compile the device headers gptq_gguf_toolkit_b200/csrc/kquant.cuh and kquant_bf16.cuh for the CPU,
+// so that the K-quant arithmetic of the product source is checked against the reference goldens without a GPU
+// (tests/test_kquant_source_cpu.py, tests/test_kquant_bf16_source_cpu.py).  It stands in for common.cuh with just what they use; every CUDA
 // intrinsic maps to the IEEE operation it denotes (compile with -ffp-contract=off).
 #pragma once
 #include <cmath>
@@ -32,23 +32,15 @@ static inline float __bfloat162float(__nv_bfloat16 b) { uint32_t u = (uint32_t)b
 struct __half { _Float16 v; };
 static inline __half __float2half_rn(float x) { return __half{(_Float16)x}; }
 static inline uint16_t __half_as_ushort(__half h) { uint16_t b; std::memcpy(&b, &h.v, 2); return b; }
-
-// torch Tensor.sum(dim=1) over GS in {16,32}: 8 lane accumulators folded in order (same as kquant.cuh)
-template <int GS, class F> inline float kq_sum8(F f) {
-    float s = 0.0f;
-    for (int l = 0; l < 8; ++l) {
-        float a = f(l);
-        for (int k = l + 8; k < GS; k += 8) a = __fadd_rn(a, f(k));
-        s = __fadd_rn(s, a);
-    }
-    return s;
-}
+static inline __half __ushort_as_half(uint16_t b) { __half h; std::memcpy(&h.v, &b, 2); return h; }
+static inline float __half2float(__half h) { return (float)h.v; }
 
 // the format constants kquant_bf16.cuh reads (GGML_QUANT_SIZES, quant_utils.py:19-26)
 enum { GQ_Q2_K = 10, GQ_Q3_K = 11, GQ_Q4_K = 12, GQ_Q5_K = 13, GQ_Q6_K = 14 };
 template <int QT> struct Fmt;
-template <> struct Fmt<GQ_Q2_K> { static constexpr int BITS = 2, GS = 16, SMQ = 15; static constexpr bool ASYM = true; };
-template <> struct Fmt<GQ_Q3_K> { static constexpr int BITS = 3, GS = 16, SMQ = 31; static constexpr bool ASYM = false; };
-template <> struct Fmt<GQ_Q4_K> { static constexpr int BITS = 4, GS = 32, SMQ = 63; static constexpr bool ASYM = true; };
-template <> struct Fmt<GQ_Q5_K> { static constexpr int BITS = 5, GS = 32, SMQ = 63; static constexpr bool ASYM = true; };
-template <> struct Fmt<GQ_Q6_K> { static constexpr int BITS = 6, GS = 16, SMQ = 63; static constexpr bool ASYM = false; };
+// (copied from csrc/common.cuh; tests/test_kquant_source_cpu.py::test_shim_format_table_matches_common_cuh keeps them in step)
+template <> struct Fmt<GQ_Q2_K> { static constexpr int BITS = 2, QMIN = 0, QMAX = 3, SMQ = 15, GS = 16, ASYM = 1, TS = 84; };
+template <> struct Fmt<GQ_Q3_K> { static constexpr int BITS = 3, QMIN = -4, QMAX = 3, SMQ = 31, GS = 16, ASYM = 0, TS = 110; };
+template <> struct Fmt<GQ_Q4_K> { static constexpr int BITS = 4, QMIN = 0, QMAX = 15, SMQ = 63, GS = 32, ASYM = 1, TS = 144; };
+template <> struct Fmt<GQ_Q5_K> { static constexpr int BITS = 5, QMIN = 0, QMAX = 31, SMQ = 63, GS = 32, ASYM = 1, TS = 176; };
+template <> struct Fmt<GQ_Q6_K> { static constexpr int BITS = 6, QMIN = -32, QMAX = 31, SMQ = 63, GS = 16, ASYM = 0, TS = 210; };

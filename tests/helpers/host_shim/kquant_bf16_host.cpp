@@ -2,7 +2,8 @@
 // the (rows x 256) super-block slabs of a weight: the four scale tensors of get_scale_and_zero in bf16 arithmetic.
 //   g++ -O2 -std=c++17 -ffp-contract=off -fno-fast-math -I tests/helpers/host_shim -I gptq_gguf_toolkit_b200/csrc -shared -fPIC ...
 #define GQ_HOST_SHIM 1
-#include "host_shim_intrinsics.h"   // stands in for kquant.cuh / common.cuh
+#include "host_shim_intrinsics.h"   // stands in for common.cuh
+#include "kquant.cuh"               // product header (kq_sum8 ...)
 #include "kquant_bf16.cuh"          // the product header under test
 
 template <int QT>
