@@ -1,4 +1,4 @@
-// kquant_bf16.cuh -- the K-quant scale search in the reference's BF16 arithmetic (EXPERIMENTAL: written at the end of round 1
+// kquant_bf16.cuh -- the K-quant scale search in the reference's BF16 (or FP16) arithmetic (EXPERIMENTAL: written at the end of round 1
 // after the GPU budget was spent; the CPU restatement of the same arithmetic that the tests check against is pinned bit for
 // bit to the reference -- tests/golden/rtn_bf16.npz -- and is what this code has to match on the first GPU run of round 2).
 //
@@ -14,17 +14,26 @@
 #include "kquant.cuh"
 #endif
 
-__device__ __forceinline__ float rb16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
-
-template <int GS, class F> __device__ __forceinline__ float kqb_sum(F f) {      // fp32 accumulation, ONE rounding at the end
-    return rb16(kq_sum8<GS>(f));
+// RND: the weight's dtype (GQ_BF16 / GQ_F16 codes of gq.h: 2 = bf16, 1 = fp16); every op of the search rounds to it.
+// The fp16 rule set is the same one (pinned against the reference on CPU as well: tests/golden/rtn_f16.npz).
+#define GQ_RND_BF16 2
+#define GQ_RND_F16 1
+template <int RND> __device__ __forceinline__ float rbn(float x) {
+    if constexpr (RND == GQ_RND_BF16) return __bfloat162float(__float2bfloat16_rn(x));
+    else return __half2float(__float2half_rn(x));
 }
+#define rb16(x) rbn<RND>(x)
 
-template <int GS, int MAXQ>
+template <int GS, int RND, class F> __device__ __forceinline__ float kqb_sum_(F f) {      // fp32 accumulation, ONE rounding at the end
+    return rbn<RND>(kq_sum8<GS>(f));
+}
+#define kqb_sum kqb_sum_
+
+template <int GS, int MAXQ, int RND>
 __device__ __forceinline__ void kqb_search_asym(const float (&x)[GS], const SearchParams &sp, float &out_scale, float &out_zero) {
     const float fmaxq = (float)MAXQ;
     const float eps_t = rb16(GQ_EPS);                                                           // clamp_min(eps) on a bf16 tensor
-    const float sum_x2 = kqb_sum<GS>([&](int k) { return rb16(__fmul_rn(x[k], x[k])); });     // :203
+    const float sum_x2 = kqb_sum<GS, RND>([&](int k) { return rb16(__fmul_rn(x[k], x[k])); });     // :203
     const float av_x = rb16(__fsqrt_rn(rb16(__fdiv_rn(sum_x2, (float)GS))));                    // :204
     float w[GS];
     float mn = x[0], mx = x[0];
@@ -36,12 +45,12 @@ __device__ __forceinline__ void kqb_search_asym(const float (&x)[GS], const Sear
     }
     mn = fminf(mn, 0.0f);                                                                       // :210
     const bool isconst = (mx == mn);                                                            // :211
-    const float sum_w = kqb_sum<GS>([&](int k) { return w[k]; });                               // :214
-    const float sum_x = kqb_sum<GS>([&](int k) { return rb16(__fmul_rn(w[k], x[k])); });      // :215
+    const float sum_w = kqb_sum<GS, RND>([&](int k) { return w[k]; });                               // :214
+    const float sum_x = kqb_sum<GS, RND>([&](int k) { return rb16(__fmul_rn(w[k], x[k])); });      // :215
     float scale = rb16(__fdiv_rn(rb16(__fsub_rn(mx, mn)), fmaxq));                              // :218
     if (isconst) scale = 0.0f;                                                                  // :219
     const float iscale = rb16(__frcp_rn(fmaxf(scale, eps_t)));                                  // :220
-    float best_err = kqb_sum<GS>([&](int k) {                                                   // :223-232
+    float best_err = kqb_sum<GS, RND>([&](int k) {                                                   // :223-232
         float q = clampf(rintf(rb16(__fmul_rn(rb16(__fsub_rn(x[k], mn)), iscale))), 0.0f, fmaxq);
         if (isconst) q = 0.0f;
         const float diff = rb16(__fsub_rn(rb16(__fadd_rn(rb16(__fmul_rn(scale, q)), mn)), x[k]));
@@ -59,12 +68,12 @@ __device__ __forceinline__ void kqb_search_asym(const float (&x)[GS], const Sear
                 const float qf = clampf(rintf(rb16(__fmul_rn(rb16(__fsub_rn(x[k], xmin)), is))), 0.0f, fmaxq);  // :242
                 L[k] = isconst ? 0.0f : qf;                                                                       // :243
             }
-            const float s_l = kqb_sum<GS>([&](int k) { return rb16(__fmul_rn(w[k], L[k])); });                  // :245
-            const float s_l2 = kqb_sum<GS>([&](int k) {                                                           // :246
+            const float s_l = kqb_sum<GS, RND>([&](int k) { return rb16(__fmul_rn(w[k], L[k])); });                  // :245
+            const float s_l2 = kqb_sum<GS, RND>([&](int k) {                                                           // :246
                 const int l = (int)L[k];
                 return rb16(__fmul_rn(w[k], (float)((l * l) & 255)));      // uint8 ** 2 wraps mod 256
             });
-            const float s_xl = kqb_sum<GS>([&](int k) { return rb16(__fmul_rn(rb16(__fmul_rn(w[k], x[k])), L[k])); });   // :247
+            const float s_xl = kqb_sum<GS, RND>([&](int k) { return rb16(__fmul_rn(rb16(__fmul_rn(w[k], x[k])), L[k])); });   // :247
             const float D = rb16(__fsub_rn(rb16(__fmul_rn(sum_w, s_l2)), rb16(__fmul_rn(s_l, s_l))));                  // :249
             // (no whole-call skip of a candidate, like the fp32 search: see gq.h search_flags)
             float sc = rb16(__fdiv_rn(rb16(__fsub_rn(rb16(__fmul_rn(sum_w, s_xl)), rb16(__fmul_rn(sum_x, s_l)))), D));  // :254
@@ -73,7 +82,7 @@ __device__ __forceinline__ void kqb_search_asym(const float (&x)[GS], const Sear
                 sc = rb16(__fdiv_rn(s_xl, fmaxf(s_l2, eps_t)));
                 m2 = 0.0f;
             }
-            const float cand = kqb_sum<GS>([&](int k) {                                                                  // :262-264
+            const float cand = kqb_sum<GS, RND>([&](int k) {                                                                  // :262-264
                 const float diff = rb16(__fsub_rn(rb16(__fadd_rn(rb16(__fmul_rn(sc, L[k])), m2)), x[k]));
                 return rb16(__fmul_rn(w[k], rb16(__fmul_rn(diff, diff))));
             });
@@ -88,7 +97,7 @@ __device__ __forceinline__ void kqb_search_asym(const float (&x)[GS], const Sear
     out_zero = -xmin;                                                                                                    // :273
 }
 
-template <int GS, int MAXQ>
+template <int GS, int MAXQ, int RND>
 __device__ __forceinline__ void kqb_search_sym(const float (&x)[GS], float &out_scale, float &out_zero) {
     float mn = x[0], mx = x[0];
 #pragma unroll
@@ -101,7 +110,7 @@ __device__ __forceinline__ void kqb_search_sym(const float (&x)[GS], float &out_
 }
 
 // Super-block double quantisation of the group scales (quant_utils.py:117-143) for ONE row, bf16 arithmetic.
-template <int QT>
+template <int QT, int RND>
 __device__ __forceinline__ void kqb_row_finalize(const float *gs, const float *gz, uint16_t &d_bits, uint16_t &dmin_bits,
                                                  uint8_t *sq, uint8_t *zq) {
     constexpr int GPR = GQ_QK_K / Fmt<QT>::GS;
@@ -119,3 +128,6 @@ __device__ __forceinline__ void kqb_row_finalize(const float *gs, const float *g
         zq[g] = (uint8_t)(int)clampf(rintf(rb16(__fmul_rn(inv_z, gz[g]))), 0.0f, smq);            // :138-143
     }
 }
+
+#undef rb16
+#undef kqb_sum

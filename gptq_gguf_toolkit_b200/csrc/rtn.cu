@@ -103,10 +103,10 @@ template <int QT> int launch_rtn(const RtnParams &p, cudaStream_t st) {
     return GQ_OK;
 }
 
-// EXPERIMENTAL twin of rtn_kernel for BF16 weights with the reference's bf16-arithmetic scale search (kquant_bf16.cuh);
+// EXPERIMENTAL twin of rtn_kernel for BF16 / FP16 weights with the reference's scale search in that dtype's arithmetic (kquant_bf16.cuh);
 // everything after the search -- quantize() in fp32, codes, GGUF bytes, dequantised weights -- is the same code.
 // Reached only through gq_rtn_quantize_native; gq_rtn_quantize (fp32 search on widened weights) is untouched.
-template <int QT>
+template <int QT, int RND>
 __global__ void __launch_bounds__(NT) rtn_bf16_kernel(const RtnParams p) {
     __shared__ RtnSmem sm;
     constexpr int GS = Fmt<QT>::GS, GPR = GQ_QK_K / GS, V = GS / 4;
@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(NT) rtn_bf16_kernel(const RtnParams p) {
         const int row = id >> 6, c4 = id & 63;
         const long base = (long)min(r0 + row, p.d_row - 1) * p.ld_in + c + 4 * c4;
         float4 v;
-        v.x = load_as_f32(p.W, base + 0, GQ_BF16); v.y = load_as_f32(p.W, base + 1, GQ_BF16);
-        v.z = load_as_f32(p.W, base + 2, GQ_BF16); v.w = load_as_f32(p.W, base + 3, GQ_BF16);
+        v.x = load_as_f32(p.W, base + 0, RND); v.y = load_as_f32(p.W, base + 1, RND);      // RND == the gq_dtype code
+        v.z = load_as_f32(p.W, base + 2, RND); v.w = load_as_f32(p.W, base + 3, RND);
         *reinterpret_cast<float4 *>(sm.Wt + wt_idx4(row, c4)) = v;
     }
     __syncthreads();
@@ -131,15 +131,15 @@ __global__ void __launch_bounds__(NT) rtn_bf16_kernel(const RtnParams p) {
             x[4 * v + 0] = t.x; x[4 * v + 1] = t.y; x[4 * v + 2] = t.z; x[4 * v + 3] = t.w;
         }
         float s, z;
-        if constexpr (Fmt<QT>::ASYM) kqb_search_asym<GS, MAXQ>(x, p.sp, s, z);
-        else kqb_search_sym<GS, MAXQ>(x, s, z);
+        if constexpr (Fmt<QT>::ASYM) kqb_search_asym<GS, MAXQ, RND>(x, p.sp, s, z);
+        else kqb_search_sym<GS, MAXQ, RND>(x, s, z);
         sm.gsc[row * 16 + g] = s;
         sm.gzr[row * 16 + g] = z;
     }
     __syncthreads();
     if (tid < R) {
         uint16_t db, dmb;
-        kqb_row_finalize<QT>(sm.gsc + tid * 16, sm.gzr + tid * 16, db, dmb, sm.rs.sq[tid], sm.rs.zq[tid]);
+        kqb_row_finalize<QT, RND>(sm.gsc + tid * 16, sm.gzr + tid * 16, db, dmb, sm.rs.sq[tid], sm.rs.zq[tid]);
         sm.rs.dbits[tid] = db;
         sm.rs.dmbits[tid] = dmb;
         sm.rs.d[tid] = __half2float(__ushort_as_half(db));
@@ -173,7 +173,9 @@ __global__ void __launch_bounds__(NT) rtn_bf16_kernel(const RtnParams p) {
 
 template <int QT> int launch_rtn_bf16(const RtnParams &p, cudaStream_t st) {
     dim3 grid((p.d_row + R - 1) / R, p.nsb);
-    rtn_bf16_kernel<QT><<<grid, NT, 0, st>>>(p);
+    static_assert(GQ_RND_BF16 == GQ_BF16 && GQ_RND_F16 == GQ_F16, "rounding codes are the gq_dtype codes");
+    if (p.w_dtype == GQ_BF16) rtn_bf16_kernel<QT, GQ_RND_BF16><<<grid, NT, 0, st>>>(p);
+    else rtn_bf16_kernel<QT, GQ_RND_F16><<<grid, NT, 0, st>>>(p);
     gq_count_launches(1);
     GQ_CHECK_CUDA(cudaGetLastError());
     return GQ_OK;
@@ -257,12 +259,12 @@ extern "C" int gq_rtn_quantize(const void *W, int w_dtype, int d_row, int d_col,
     return dispatch_rtn(qtype, p, (cudaStream_t)stream);
 }
 
-// EXPERIMENTAL (see kquant_bf16.cuh): gq_rtn_quantize for a BF16 weight with the scale search in the reference's bf16
-// arithmetic -- what quantizer.py:278-330 computes for embed_tokens / lm_head of a bf16 model.  Same outputs and conventions.
+// EXPERIMENTAL (see kquant_bf16.cuh): gq_rtn_quantize for a BF16 / FP16 weight with the scale search in the weight's own
+// arithmetic -- what quantizer.py:278-330 computes for embed_tokens / lm_head of a 16-bit model.  Same outputs and conventions.
 extern "C" int gq_rtn_quantize_native(const void *W, int w_dtype, int d_row, int d_col, int qtype, double rmin,
                                       double rdelta, int nstep, void *qweight, uint16_t *d, void *sq, uint16_t *dmin,
                                       void *zq, uint8_t *packed, void *wdeq, int wdeq_dtype, gq_stream_t stream) {
-    if (w_dtype != GQ_BF16)      // fp32 weights: the native arithmetic IS the fp32 search; fp16 is not pinned
+    if (w_dtype == GQ_F32)       // fp32 weights: the native arithmetic IS the fp32 search
         return gq_rtn_quantize(W, w_dtype, d_row, d_col, qtype, rmin, rdelta, nstep, qweight, d, sq, dmin, zq, packed, wdeq,
                                wdeq_dtype, stream);
     FmtInfo f;

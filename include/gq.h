@@ -155,8 +155,8 @@ GQ_API int gq_rtn_quantize(const void *W, int w_dtype, int d_row, int d_col, int
 
 /* EXPERIMENTAL (not yet validated on hardware; the CPU oracle's twin is pinned to the reference, tests/golden/rtn_bf16.npz):
  * gq_rtn_quantize with the scale search in the arithmetic of the weight's own dtype, as the reference does it
- * (quantizer.py:303-305 passes the weight un-widened): for GQ_BF16 every op of the search rounds to bf16; the final quantize()
- * is fp32 as in the reference.  Other dtypes fall through to gq_rtn_quantize.  Same arguments and outputs. */
+ * (quantizer.py:303-305 passes the weight un-widened): for GQ_BF16 / GQ_F16 every op of the search rounds to that dtype; the final
+ * quantize() is fp32 as in the reference.  GQ_F32 falls through to gq_rtn_quantize.  Same arguments and outputs. */
 GQ_API int gq_rtn_quantize_native(const void *W, int w_dtype, int d_row, int d_col, int qtype,
                     double rmin, double rdelta, int nstep,
                     void *qweight, uint16_t *d, void *sq, uint16_t *dmin, void *zq,

@@ -82,7 +82,7 @@ static inline float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, 
  * Pinned op by op and end to end against the reference on CPU (tests/golden/make_golden_rtn_bf16.py): all four scale
  * tensors bit-identical for the five types.  RB() is the identity in the fp32 mode, i.e. the fp32 contract is untouched.
  * The switch is a file-scope flag set by the entry point (test infrastructure: not re-entrant). */
-static int g_bf16 = 0;
+static int g_bf16 = 0;      /* 0: fp32 arithmetic, 1: bf16, 2: fp16 (every op rounds to that dtype) */
 static inline float bf16_rne(float x) {
     uint32_t u; memcpy(&u, &x, 4);
     if ((u & 0x7fffffffu) > 0x7f800000u) return x;                 /* NaN */
@@ -90,8 +90,8 @@ static inline float bf16_rne(float x) {
     u &= 0xffff0000u;
     float r; memcpy(&r, &u, 4); return r;
 }
-static inline float RB(float x) { return g_bf16 ? bf16_rne(x) : x; }
-#define ORC_EPS_T (g_bf16 ? bf16_rne(ORC_EPS) : ORC_EPS)          /* clamp_min(eps) on a tensor of that dtype */
+static inline float RB(float x) { return g_bf16 == 1 ? bf16_rne(x) : g_bf16 == 2 ? (float)(_Float16)x : x; }
+#define ORC_EPS_T (g_bf16 ? RB(ORC_EPS) : ORC_EPS)                /* clamp_min(eps) on a tensor of that dtype (0 in fp16) */
 
 /* ------------------------------------------------------------------------------------------
  * make_k_quants: quant_utils.py:199-274  (Q2_K, Q4_K, Q5_K; asymmetric weighted LSQ search)
@@ -452,6 +452,16 @@ int orc_rtn_quantize_bf16(const float *W, int d_row, int d_col, int qtype,
                           double rmin, double rdelta, int nstep,
                           uint8_t *qweight, uint16_t *d, uint16_t *dmin, uint8_t *sq, uint8_t *zq) {
     g_bf16 = 1;
+    const int rc = orc_rtn_quantize(W, d_row, d_col, qtype, rmin, rdelta, nstep, qweight, d, dmin, sq, zq);
+    g_bf16 = 0;
+    return rc;
+}
+/* ... and for an fp16 weight (probe only: agreement with the reference is reported by
+ * tests/golden/check_oracle_vs_reference_large.py, not asserted -- see DESIGN.md section 2). */
+int orc_rtn_quantize_fp16(const float *W, int d_row, int d_col, int qtype,
+                          double rmin, double rdelta, int nstep,
+                          uint8_t *qweight, uint16_t *d, uint16_t *dmin, uint8_t *sq, uint8_t *zq) {
+    g_bf16 = 2;
     const int rc = orc_rtn_quantize(W, d_row, d_col, qtype, rmin, rdelta, nstep, qweight, d, dmin, sq, zq);
     g_bf16 = 0;
     return rc;

@@ -114,9 +114,9 @@ def gptq_step(W: np.ndarray, U: np.ndarray, qtype: int, block_size=128, rmin=-1.
     return out + (flags,) if return_flags else out
 
 
-def rtn_quantize(W: np.ndarray, qtype: int, rmin=-1.0, rdelta=0.1, nstep=20, bf16: bool = False):
-    """quantizer.py:278-330.  Returns the 5 tensors.  bf16=True: W holds bf16 values (widened to fp32) and the scale search
-    runs in the reference's bf16 arithmetic (what it does for a bf16 model's embed_tokens / lm_head)."""
+def rtn_quantize(W: np.ndarray, qtype: int, rmin=-1.0, rdelta=0.1, nstep=20, bf16: bool = False, fp16: bool = False):
+    """quantizer.py:278-330.  Returns the 5 tensors.  bf16=True / fp16=True: W holds bf16 / fp16 values (widened to fp32) and the
+    scale search runs in that dtype's arithmetic, like the reference does for a 16-bit model's embed_tokens / lm_head."""
     W = np.ascontiguousarray(W, dtype=np.float32)
     d_row, d_col = W.shape
     f = fmt(qtype)
@@ -126,7 +126,7 @@ def rtn_quantize(W: np.ndarray, qtype: int, rmin=-1.0, rdelta=0.1, nstep=20, bf1
     dmin = np.empty((d_row, nsb), np.uint16)
     sq = np.empty((d_row, ng), np.uint8)
     zq = np.empty((d_row, ng), np.uint8)
-    fn = lib().orc_rtn_quantize_bf16 if bf16 else lib().orc_rtn_quantize
+    fn = lib().orc_rtn_quantize_bf16 if bf16 else lib().orc_rtn_quantize_fp16 if fp16 else lib().orc_rtn_quantize
     rc = fn(
         _p(W, C.c_float), C.c_int(d_row), C.c_int(d_col), C.c_int(qtype),
         C.c_double(rmin), C.c_double(rdelta), C.c_int(nstep),

@@ -57,7 +57,8 @@ def gptq_quantize(W, U, q_type, block_size=128, rmin=-1.0, rdelta=0.1, nstep=20,
 
 
 def rtn_quantize(W, q_type, rmin=-1.0, rdelta=0.1, nstep=20, packed=True, wdeq_dtype=None, native_arith=False):
-    out = orc.rtn_quantize(_np(W.float()), int(q_type), rmin, rdelta, nstep, bf16=bool(native_arith and W.dtype == torch.bfloat16))
+    out = orc.rtn_quantize(_np(W.float()), int(q_type), rmin, rdelta, nstep, bf16=bool(native_arith and W.dtype == torch.bfloat16),
+                           fp16=bool(native_arith and W.dtype == torch.float16))
     five = _five_t(out)
     pk = torch.from_numpy(orc.pack(int(q_type), *out)) if packed else None
     wd = torch.from_numpy(orc.dequantize(int(q_type), *out)).to(wdeq_dtype) if wdeq_dtype is not None else None

@@ -37,6 +37,16 @@ def main():
             out[f"{t.name}_{k}"] = a.view(np.uint16) if a.dtype == np.float16 else a
     np.savez_compressed(os.path.join(HERE, "rtn_bf16.npz"), **out)
     print("wrote rtn_bf16.npz")
+    # the same weight values rounded to fp16: the reference then searches in fp16 arithmetic (clamp_min(1e-9) is a no-op there)
+    W16 = W.float().to(torch.float16)
+    out = {"W_f16_bits": W16.view(torch.int16).numpy().view(np.uint16)}
+    for t in (T.Q2_K, T.Q3_K, T.Q4_K, T.Q5_K, T.Q6_K):
+        five = RefQuantizer._quant_non_block_module(_Self(), W16.clone(), t)
+        for k, v in zip(("qweight", "d", "sq", "dmin", "zq"), five):
+            a = v.numpy()
+            out[f"{t.name}_{k}"] = a.view(np.uint16) if a.dtype == np.float16 else a
+    np.savez_compressed(os.path.join(HERE, "rtn_f16.npz"), **out)
+    print("wrote rtn_f16.npz")
 
 
 if __name__ == "__main__":

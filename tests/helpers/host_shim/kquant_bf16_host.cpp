@@ -6,7 +6,7 @@
 #include "kquant.cuh"               // product header (kq_sum8 ...)
 #include "kquant_bf16.cuh"          // the product header under test
 
-template <int QT>
+template <int QT, int RND>
 static void run(const float *W, int d_row, int d_col, double rmin, double rdelta, int nstep, uint16_t *d, uint16_t *dmin,
                 uint8_t *sq, uint8_t *zq) {
     constexpr int GS = Fmt<QT>::GS, GPR = GQ_QK_K / GS, MAXQ = (1 << Fmt<QT>::BITS) - 1;
@@ -20,22 +20,30 @@ static void run(const float *W, int d_row, int d_col, double rmin, double rdelta
             for (int g = 0; g < GPR; ++g) {
                 float x[GS];
                 for (int k = 0; k < GS; ++k) x[k] = W[(long)r * d_col + sb * GQ_QK_K + g * GS + k];
-                if constexpr (Fmt<QT>::ASYM) kqb_search_asym<GS, MAXQ>(x, sp, gs[g], gz[g]);
-                else kqb_search_sym<GS, MAXQ>(x, gs[g], gz[g]);
+                if constexpr (Fmt<QT>::ASYM) kqb_search_asym<GS, MAXQ, RND>(x, sp, gs[g], gz[g]);
+                else kqb_search_sym<GS, MAXQ, RND>(x, gs[g], gz[g]);
             }
-            kqb_row_finalize<QT>(gs, gz, d[(long)r * nsb + sb], dmin[(long)r * nsb + sb], sq + (long)r * ng + sb * GPR,
+            kqb_row_finalize<QT, RND>(gs, gz, d[(long)r * nsb + sb], dmin[(long)r * nsb + sb], sq + (long)r * ng + sb * GPR,
                                  zq + (long)r * ng + sb * GPR);
         }
 }
 
-extern "C" int host_scales_bf16(int qtype, const float *W, int d_row, int d_col, double rmin, double rdelta, int nstep,
-                                uint16_t *d, uint16_t *dmin, uint8_t *sq, uint8_t *zq) {
+template <int RND>
+static int dispatch(int qtype, const float *W, int d_row, int d_col, double rmin, double rdelta, int nstep, uint16_t *d, uint16_t *dmin,
+                    uint8_t *sq, uint8_t *zq) {
     switch (qtype) {
-    case GQ_Q2_K: run<GQ_Q2_K>(W, d_row, d_col, rmin, rdelta, nstep, d, dmin, sq, zq); return 0;
-    case GQ_Q3_K: run<GQ_Q3_K>(W, d_row, d_col, rmin, rdelta, nstep, d, dmin, sq, zq); return 0;
-    case GQ_Q4_K: run<GQ_Q4_K>(W, d_row, d_col, rmin, rdelta, nstep, d, dmin, sq, zq); return 0;
-    case GQ_Q5_K: run<GQ_Q5_K>(W, d_row, d_col, rmin, rdelta, nstep, d, dmin, sq, zq); return 0;
-    case GQ_Q6_K: run<GQ_Q6_K>(W, d_row, d_col, rmin, rdelta, nstep, d, dmin, sq, zq); return 0;
+    case GQ_Q2_K: run<GQ_Q2_K, RND>(W, d_row, d_col, rmin, rdelta, nstep, d, dmin, sq, zq); return 0;
+    case GQ_Q3_K: run<GQ_Q3_K, RND>(W, d_row, d_col, rmin, rdelta, nstep, d, dmin, sq, zq); return 0;
+    case GQ_Q4_K: run<GQ_Q4_K, RND>(W, d_row, d_col, rmin, rdelta, nstep, d, dmin, sq, zq); return 0;
+    case GQ_Q5_K: run<GQ_Q5_K, RND>(W, d_row, d_col, rmin, rdelta, nstep, d, dmin, sq, zq); return 0;
+    case GQ_Q6_K: run<GQ_Q6_K, RND>(W, d_row, d_col, rmin, rdelta, nstep, d, dmin, sq, zq); return 0;
     }
     return -1;
+}
+
+// rnd: 2 = bf16, 1 = fp16 (the gq_dtype codes)
+extern "C" int host_scales_native(int rnd, int qtype, const float *W, int d_row, int d_col, double rmin, double rdelta, int nstep,
+                                  uint16_t *d, uint16_t *dmin, uint8_t *sq, uint8_t *zq) {
+    return rnd == 2 ? dispatch<GQ_RND_BF16>(qtype, W, d_row, d_col, rmin, rdelta, nstep, d, dmin, sq, zq)
+                    : dispatch<GQ_RND_F16>(qtype, W, d_row, d_col, rmin, rdelta, nstep, d, dmin, sq, zq);
 }

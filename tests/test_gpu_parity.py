@@ -387,13 +387,15 @@ def test_full_size_properties(ops):
 
 @pytest.mark.skipif(os.environ.get("GQ_TEST_EXPERIMENTAL") != "1",
                     reason="gq_rtn_quantize_native is experimental and not yet validated on hardware (set GQ_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
 @pytest.mark.parametrize("tname", list(TYPES))
-def test_rtn_native_bf16_arithmetic_matches_reference_golden(ops, golden_dir, tname):
-    """embed_tokens / lm_head of a bf16 model: the reference searches the scales in bf16 arithmetic (quantizer.py:303-305);
-    tests/golden/rtn_bf16.npz holds its output, the oracle's bf16 mode already matches it bit for bit."""
-    g = np.load(os.path.join(golden_dir, "rtn_bf16.npz"))
-    W = torch.from_numpy(g["W_bf16_bits"].view(np.int16).copy()).view(torch.bfloat16).cuda()
-    out = ops.rtn_quantize(W, TYPES[tname], wdeq_dtype=torch.bfloat16, native_arith=True)
+def test_rtn_native_bf16_arithmetic_matches_reference_golden(ops, golden_dir, tname, dtype):
+    """embed_tokens / lm_head of a 16-bit model: the reference searches the scales in the weight's own arithmetic
+    (quantizer.py:303-305); tests/golden/rtn_{bf16,f16}.npz hold its output, the oracle's modes already match bit for bit."""
+    g = np.load(os.path.join(golden_dir, f"rtn_{dtype}.npz"))
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float16
+    W = torch.from_numpy(g[f"W_{dtype}_bits"].view(np.int16).copy()).view(tdt).cuda()
+    out = ops.rtn_quantize(W, TYPES[tname], wdeq_dtype=tdt, native_arith=True)
     torch.cuda.synchronize()
     assert_five_equal(out[:5], [g[f"{tname}_{k}"] for k in KEYS], f"rtn bf16 native/{tname}")
     ref5 = [g[f"{tname}_{k}"] for k in KEYS]

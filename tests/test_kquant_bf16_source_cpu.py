@@ -24,10 +24,14 @@ def host_lib(tmp_path_factory):
     return C.CDLL(so)
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
 @pytest.mark.parametrize("tname", ["Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"])
-def test_device_source_matches_reference_golden(host_lib, golden_dir, tname):
-    g = np.load(os.path.join(golden_dir, "rtn_bf16.npz"))
-    W = np.ascontiguousarray((g["W_bf16_bits"].astype(np.uint32) << 16).view(np.float32))
+def test_device_source_matches_reference_golden(host_lib, golden_dir, tname, dtype):
+    g = np.load(os.path.join(golden_dir, f"rtn_{dtype}.npz"))
+    if dtype == "bf16":
+        W = np.ascontiguousarray((g["W_bf16_bits"].astype(np.uint32) << 16).view(np.float32))
+    else:
+        W = np.ascontiguousarray(g["W_f16_bits"].view(np.float16).astype(np.float32))
     qt = {"Q2_K": 10, "Q3_K": 11, "Q4_K": 12, "Q5_K": 13, "Q6_K": 14}[tname]
     gs = 32 if tname in ("Q4_K", "Q5_K") else 16
     d_row, d_col = W.shape
@@ -36,7 +40,7 @@ def test_device_source_matches_reference_golden(host_lib, golden_dir, tname):
     sq = np.zeros((d_row, d_col // gs), np.uint8)
     zq = np.zeros_like(sq)
     p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
-    rc = host_lib.host_scales_bf16(C.c_int(qt), p(W, C.c_float), C.c_int(d_row), C.c_int(d_col), C.c_double(-1.0), C.c_double(0.1),
+    rc = host_lib.host_scales_native(C.c_int(2 if dtype == "bf16" else 1), C.c_int(qt), p(W, C.c_float), C.c_int(d_row), C.c_int(d_col), C.c_double(-1.0), C.c_double(0.1),
                                    C.c_int(20), p(d, C.c_uint16), p(dmin, C.c_uint16), p(sq, C.c_uint8), p(zq, C.c_uint8))
     assert rc == 0
     assert np.array_equal(d, g[f"{tname}_d"]), "super_group_scale"

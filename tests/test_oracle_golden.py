@@ -150,3 +150,15 @@ def test_rtn_bf16_arithmetic_matches_reference_golden(golden_dir, tname):
     same = float((out32[0] == out[0]).mean())
     assert same < 1.0, "the fp32-arithmetic search is expected to differ from the bf16 one on this input"
     assert same > 0.85, same          # measured 0.896 (Q4_K) ... 0.990 (Q3_K)
+
+
+@pytest.mark.parametrize("tname", ["Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"])
+def test_rtn_fp16_arithmetic_matches_reference_golden(golden_dir, tname):
+    """The same for an FP16 weight (tests/golden/rtn_f16.npz): same rule set, rounding to fp16."""
+    g = np.load(os.path.join(golden_dir, "rtn_f16.npz"))
+    W = g["W_f16_bits"].view(np.float16).astype(np.float32)
+    qt = {"Q2_K": 10, "Q3_K": 11, "Q4_K": 12, "Q5_K": 13, "Q6_K": 14}[tname]
+    out = orc.rtn_quantize(W, qt, fp16=True)
+    for k, a in zip(("qweight", "d", "sq", "dmin", "zq"), out):
+        a = a.view(np.uint16) if a.dtype == np.float16 else a
+        assert np.array_equal(a.view(np.uint8), g[f"{tname}_{k}"].view(np.uint8)), f"{tname}.{k}"
