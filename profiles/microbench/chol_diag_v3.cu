@@ -19,7 +19,9 @@
 #include <cstdlib>
 #include <vector>
 
+#ifndef SIMT_EMU          // tests/test_simt_emu_cpu.py runs the kernel below on the host (tests/helpers/simt_emu)
 #include <cuda_runtime.h>
+#endif
 
 constexpr int NB = 128, LS = 132, PW = 32, T3 = 256;
 struct Smem3 { float L[NB * LS]; float X[NB * LS]; float col[2][NB]; float inv[NB]; float d[NB]; };
@@ -185,6 +187,7 @@ __global__ void __launch_bounds__(T3) chol_diag_v3_kernel(float *A, float *Binv,
     }
 }
 
+#ifndef SIMT_EMU
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e_), __LINE__); return 1; } } while (0)
 
 int main() {
@@ -255,3 +258,4 @@ int main() {
            1e3 * ms / reps);
     return ok ? 0 : 2;
 }
+#endif  // SIMT_EMU

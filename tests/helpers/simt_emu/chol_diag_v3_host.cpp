@@ -1,0 +1,12 @@
+// TEST-ONLY: profiles/microbench/chol_diag_v3.cu (a kernel that has not run on a GPU yet) on the SIMT emulator.
+#define SIMT_EMU 1
+#include "simt_emu.h"
+alignas(16) unsigned char raw[160 * 1024];          // the kernel's `extern __shared__ ... raw[]`
+#include "chol_diag_v3.cu"
+
+// A: (n x n) row-major with the 128 x 128 SPD block at (k0, k0); outputs like the kernel's.
+extern "C" int run_chol_diag_v3(float *A, float *Binv, float *BinvT, long ld, int k0, int *not_pd) {
+    static_assert(sizeof(Smem3) <= sizeof(raw), "shared memory array too small");
+    simt::launch(dim3(1), dim3(T3), [&]() { chol_diag_v3_kernel(A, Binv, BinvT, ld, k0, not_pd); });
+    return 0;
+}
