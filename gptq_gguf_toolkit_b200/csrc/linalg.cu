@@ -14,6 +14,7 @@
 #include <mutex>
 #include <vector>
 
+#include "chol_diag_v3.cuh"
 #include "gemm_tf32.cuh"
 #include "sgemm.cuh"
 
@@ -468,9 +469,9 @@ LookaheadCtx *lookahead_ctx(cudaStream_t st, size_t n_events) {
     }
     return &c;
 }
-bool prepare_diag_v2() {      // read on every call: tests and micro-benchmarks flip it at run time
-    const char *e = getenv("GQ_DIAG_V2");
-    return !(e && e[0] == '0');
+int prepare_diag_variant() {      // GQ_DIAG_V2: 0 = chol_diag_kernel, 1 (default) = chol_diag_v2_kernel, 3 = experimental chol_diag_v3.cuh
+    const char *e = getenv("GQ_DIAG_V2");      // read on every call: tests and micro-benchmarks flip it at run time
+    return (e && e[0] == '0') ? 0 : (e && e[0] == '3') ? 3 : 1;
 }
 bool prepare_use_simt() {
     static int v = -1;
@@ -524,7 +525,9 @@ extern "C" int gq_prepare(float *H, const float *W, int d_row, int d_col, float 
     if (!simt) GQ_CHECK_CUDA(cudaMemsetAsync(LiT, 0, (size_t)n * n * sizeof(float), st));
     GQ_CHECK_CUDA(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DiagSmem)));
     GQ_CHECK_CUDA(cudaFuncSetAttribute(chol_diag_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DiagSmem2)));
-    const bool diag_v2 = prepare_diag_v2();
+    const int diag_variant = prepare_diag_variant();
+    if (diag_variant == 3)
+        GQ_CHECK_CUDA(cudaFuncSetAttribute(cd3::chol_diag_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cd3::Smem3)));
     auto tc_gemm_on = [&](cudaStream_t stream_, void *ws_, const float *Ap, const float *Bp, float *Cp, int M, int N, int K, int batch,
                           long ab, long bb, long cb, float alpha, float beta, int tile_mode, int k_mode, bool same) {
         tg::GemmArgs g;
@@ -546,7 +549,8 @@ extern "C" int gq_prepare(float *H, const float *W, int d_row, int d_col, float 
     }
     int la_prev_b = -1;      // index of the event recorded after the previous step's rest-of-trailing update
     for (int k0 = 0; k0 < n; k0 += NB) {
-        if (diag_v2) chol_diag_v2_kernel<<<1, DT2, sizeof(DiagSmem2), st>>>(A, Li, simt ? nullptr : LiT, ld, k0, flag);
+        if (diag_variant == 1) chol_diag_v2_kernel<<<1, DT2, sizeof(DiagSmem2), st>>>(A, Li, simt ? nullptr : LiT, ld, k0, flag);
+        else if (diag_variant == 3) cd3::chol_diag_v3_kernel<<<1, cd3::T3, sizeof(cd3::Smem3), st>>>(A, Li, simt ? nullptr : LiT, ld, k0, flag);
         else chol_diag_kernel<<<1, DT, sizeof(DiagSmem), st>>>(A, Li, simt ? nullptr : LiT, ld, k0, flag);
         gq_count_launches(1);
         const int rem = n - k0 - NB;

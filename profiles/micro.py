@@ -62,7 +62,7 @@ def main():
         for n in (4096, 14336):
             H0 = spd(n)
             W = torch.randn(256, n, device="cuda")
-            for v in ("1", "0"):        # chol_diag_v2_kernel (default) vs the original diagonal kernel
+            for v in ("1", "0") + (("3",) if "experimental" in what else ()):   # v2 (default), the original, experimental v3
                 os.environ["GQ_DIAG_V2"] = v
                 l0 = ops.launch_count()
                 mn, av = timed(lambda: ops.prepare(H0.clone(), W, 0.01), warm=1, it=2)

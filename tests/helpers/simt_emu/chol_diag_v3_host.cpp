@@ -1,8 +1,9 @@
-// TEST-ONLY: profiles/microbench/chol_diag_v3.cu (a kernel that has not run on a GPU yet) on the SIMT emulator.
+// TEST-ONLY: gptq_gguf_toolkit_b200/csrc/chol_diag_v3.cuh (a kernel that has not run on a GPU yet) on the SIMT emulator.
 #define SIMT_EMU 1
 #include "simt_emu.h"
 alignas(16) unsigned char raw[160 * 1024];          // the kernel's `extern __shared__ ... raw[]`
-#include "chol_diag_v3.cu"
+#include "chol_diag_v3.cuh"
+using namespace cd3;
 
 // A: (n x n) row-major with the 128 x 128 SPD block at (k0, k0); outputs like the kernel's.
 extern "C" int run_chol_diag_v3(float *A, float *Binv, float *BinvT, long ld, int k0, int *not_pd) {

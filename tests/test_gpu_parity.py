@@ -259,7 +259,10 @@ def _spd_problem(n, d_row, seed):
     return H, W
 
 
-@pytest.fixture(params=["1", "0"], ids=["diag_v2", "diag_v1"])
+_DIAG = [("1", "diag_v2"), ("0", "diag_v1")] + ([("3", "diag_v3_experimental")] if os.environ.get("GQ_TEST_EXPERIMENTAL") == "1" else [])
+
+
+@pytest.fixture(params=[v for v, _ in _DIAG], ids=[n for _, n in _DIAG])
 def diag_variant(request, monkeypatch):
     """Both diagonal-block kernels of gq_prepare (csrc/linalg.cu: chol_diag_v2_kernel, the default, and the original
     chol_diag_kernel) must meet the same B2 bounds; the library reads GQ_DIAG_V2 on every call."""

@@ -1,6 +1,6 @@
 """Kernels written without GPU access, run on the host through a small SIMT emulator (tests/helpers/simt_emu: one fiber per
 CUDA thread, __syncthreads() = barrier between fibers) to catch indexing / algorithm mistakes before they cost GPU minutes.
-Covered: profiles/microbench/chol_diag_v3.cu, the register-resident diagonal-block kernel proposed for gq_prepare in round 2
+Covered: gptq_gguf_toolkit_b200/csrc/chol_diag_v3.cuh, the register-resident diagonal-block kernel (GQ_DIAG_V2=3, experimental)
 (128 x 128 Cholesky factor + its inverse + the inverse's transpose, against a double-precision factorisation)."""
 import ctypes as C
 import os
@@ -17,7 +17,7 @@ EMU = os.path.join(ROOT, "tests", "helpers", "simt_emu")
 def lib(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("emu") / "libchol_v3_emu.so")
     cmd = ["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-x", "c++", "-I", EMU,
-           "-I", os.path.join(ROOT, "profiles", "microbench"), os.path.join(EMU, "chol_diag_v3_host.cpp"), "-o", so]
+           "-I", os.path.join(ROOT, "gptq_gguf_toolkit_b200", "csrc"), os.path.join(EMU, "chol_diag_v3_host.cpp"), "-o", so]
     out = subprocess.run(cmd, capture_output=True, text=True)
     assert out.returncode == 0, out.stderr[-4000:]
     return C.CDLL(so)
