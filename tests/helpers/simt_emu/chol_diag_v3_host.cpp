@@ -1,7 +1,7 @@
 // TEST-ONLY: gptq_gguf_toolkit_b200/csrc/chol_diag_v3.cuh (a kernel that has not run on a GPU yet) on the SIMT emulator.
 #define SIMT_EMU 1
 #include "simt_emu.h"
-alignas(16) unsigned char raw[160 * 1024];          // the kernel's `extern __shared__ ... raw[]`
+namespace cd3 { alignas(16) unsigned char raw[160 * 1024]; }   // the kernel's `extern __shared__ ... raw[]` (declared inside namespace cd3)
 #include "chol_diag_v3.cuh"
 using namespace cd3;
 
