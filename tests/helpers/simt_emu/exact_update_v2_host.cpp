@@ -1,12 +1,30 @@
 // TEST-ONLY: gptq_gguf_toolkit_b200/csrc/exact_update_v2.cuh (an experimental kernel that has not run on a GPU yet) on the SIMT
-// emulator.  cp.async is emulated by an immediate 16-byte copy (so a missing wait would NOT be noticed; wrong indices are).
+// emulator.  cp.async is emulated AS LATE AS LEGAL: a copy is only performed when a cp_async_wait<N> of the issuing thread
+// retires its group (all but the newest N committed groups), so that reading a pipeline stage before the wait that covers it
+// -- or waiting for too few groups -- shows up as stale data and a bit mismatch.
 #define SIMT_EMU 1
 #include "simt_emu.h"
 #include <algorithm>
+#include <deque>
+#include <map>
+#include <utility>
 using std::min;
-static inline void cp_async16(void *dst, const void *src) { std::memcpy(dst, src, 16); }
-static inline void cp_async_commit() {}
-template <int N> static inline void cp_async_wait() {}
+namespace cpa {
+struct Copy { void *dst; const void *src; };
+struct Thread { std::vector<Copy> open; std::deque<std::vector<Copy>> groups; };
+static std::map<int, Thread> g_threads;        // keyed by the linear thread id of the block being run
+static Thread &me() { return g_threads[(int)threadIdx.x]; }
+static void reset() { g_threads.clear(); }
+}  // namespace cpa
+static inline void cp_async16(void *dst, const void *src) { cpa::me().open.push_back({dst, src}); }
+static inline void cp_async_commit() { auto &t = cpa::me(); t.groups.push_back(std::move(t.open)); t.open.clear(); }
+template <int N> static inline void cp_async_wait() {
+    auto &t = cpa::me();
+    while ((int)t.groups.size() > N) {
+        for (auto &c : t.groups.front()) std::memcpy(c.dst, c.src, 16);
+        t.groups.pop_front();
+    }
+}
 static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 alignas(16) unsigned char smem_raw[80 * 1024];       // the kernel's `extern __shared__ ... smem_raw[]`
