@@ -32,6 +32,19 @@ static inline float __bfloat162float(__nv_bfloat16 b) { uint32_t u = (uint32_t)b
 struct __half { _Float16 v; };
 static inline __half __float2half_rn(float x) { return __half{(_Float16)x}; }
 static inline uint16_t __half_as_ushort(__half h) { uint16_t b; std::memcpy(&b, &h.v, 2); return b; }
+// ---- what tile.cuh / rtn_native.cuh need on top (used together with tests/helpers/simt_emu/simt_emu.h) ----
+enum { GQ_F32 = 0, GQ_F16 = 1, GQ_BF16 = 2 };
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+struct __nv_bfloat162 { __nv_bfloat16 x, y; };
+static inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { return __nv_bfloat162{__float2bfloat16_rn(a), __float2bfloat16_rn(b)}; }
+struct __half2 { __half x, y; };
+static inline __half2 __floats2half2_rn(float a, float b) { return __half2{__float2half_rn(a), __float2half_rn(b)}; }
+static inline uint32_t __reduce_or_sync(uint32_t, uint32_t v) { return v; }      // publish_flags is not exercised on the host
+static inline uint32_t atomicOr(uint32_t *p, uint32_t v) { uint32_t o = *p; *p |= v; return o; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+
 static inline __half __ushort_as_half(uint16_t b) { __half h; std::memcpy(&h.v, &b, 2); return h; }
 static inline float __half2float(__half h) { return (float)h.v; }
 
@@ -44,3 +57,8 @@ template <> struct Fmt<GQ_Q3_K> { static constexpr int BITS = 3, QMIN = -4, QMAX
 template <> struct Fmt<GQ_Q4_K> { static constexpr int BITS = 4, QMIN = 0, QMAX = 15, SMQ = 63, GS = 32, ASYM = 1, TS = 144; };
 template <> struct Fmt<GQ_Q5_K> { static constexpr int BITS = 5, QMIN = 0, QMAX = 31, SMQ = 63, GS = 32, ASYM = 1, TS = 176; };
 template <> struct Fmt<GQ_Q6_K> { static constexpr int BITS = 6, QMIN = -32, QMAX = 31, SMQ = 63, GS = 16, ASYM = 0, TS = 210; };
+static inline float load_as_f32(const void *p, long idx, int dtype) {       // common.cuh:85-89
+    if (dtype == GQ_F32) return ((const float *)p)[idx];
+    if (dtype == GQ_F16) return __half2float(((const __half *)p)[idx]);
+    return __bfloat162float(((const __nv_bfloat16 *)p)[idx]);
+}

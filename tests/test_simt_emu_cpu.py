@@ -86,3 +86,54 @@ def test_exact_update_v2_on_the_emulator(lib_upd, d_row, d_col, c):
     lib_upd.run_exact_update_v2(p(got, C.c_float), p(U, C.c_float), C.c_int(d_row), C.c_int(d_col), C.c_int(c))
     assert np.array_equal(got[:, :c + 256], W[:, :c + 256]), "columns up to the finished super-block must not change"
     assert np.array_equal(got, ref)
+
+
+@pytest.fixture(scope="module")
+def lib_rtn(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu") / "librtn_native_emu.so")
+    cmd = ["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-I", EMU,
+           "-I", os.path.join(ROOT, "tests", "helpers", "host_shim"), "-I", os.path.join(ROOT, "gptq_gguf_toolkit_b200", "csrc"),
+           os.path.join(EMU, "rtn_native_host.cpp"), "-o", so]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-4000:]
+    return C.CDLL(so)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("tname", ["Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"])
+def test_rtn_native_kernel_on_the_emulator(lib_rtn, golden_dir, tname, dtype):
+    """gptq_gguf_toolkit_b200/csrc/rtn_native.cuh (gq_rtn_quantize_native, experimental): the WHOLE kernel -- tile load, search in
+    the weight's own arithmetic, double quantisation, fp32 quantize(), codes, GGUF bytes, 16-bit dequantised weights -- against
+    the reference golden of a bf16 / fp16 weight (five tensors), the oracle's packer and dequantiser."""
+    import torch
+    from oracle import oracle as orc
+    g = np.load(os.path.join(golden_dir, f"rtn_{dtype}.npz"))
+    bits = np.ascontiguousarray(g[f"W_{dtype}_bits"])
+    qt = {"Q2_K": 10, "Q3_K": 11, "Q4_K": 12, "Q5_K": 13, "Q6_K": 14}[tname]
+    gs = 32 if tname in ("Q4_K", "Q5_K") else 16
+    ts = {"Q2_K": 84, "Q3_K": 110, "Q4_K": 144, "Q5_K": 176, "Q6_K": 210}[tname]
+    d_row, d_col = bits.shape
+    nsb = d_col // 256
+    qw = np.zeros((d_row, d_col), np.uint8)
+    d = np.zeros((d_row, nsb), np.uint16)
+    dmin = np.zeros_like(d)
+    sq = np.zeros((d_row, d_col // gs), np.uint8)
+    zq = np.zeros_like(sq)
+    pk = np.zeros((d_row, nsb * ts), np.uint8)
+    wd = np.zeros((d_row, d_col), np.uint16)
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    rc = lib_rtn.run_rtn_native(C.c_int(2 if dtype == "bf16" else 1), C.c_int(qt), p(bits, C.c_uint16), C.c_int(d_row), C.c_int(d_col),
+                                C.c_double(-1.0), C.c_double(0.1), C.c_int(20), p(qw, C.c_uint8), p(d, C.c_uint16), p(dmin, C.c_uint16),
+                                p(sq, C.c_uint8), p(zq, C.c_uint8), p(pk, C.c_uint8), p(wd, C.c_uint16))
+    assert rc == 0
+    for k, a in (("qweight", qw), ("d", d), ("sq", sq), ("dmin", dmin), ("zq", zq)):
+        assert np.array_equal(a.view(np.uint8), g[f"{tname}_{k}"].view(np.uint8)), k
+    cd = np.uint8 if tname in ("Q2_K", "Q4_K", "Q5_K") else np.int8
+    five = (qw.view(cd), d.view(np.float16), sq.view(cd), dmin.view(np.float16), zq.view(cd))
+    assert np.array_equal(pk, orc.pack(qt, *five)), "GGUF block bytes"
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float16
+    # compared as VALUES: a code 0 that came from rint(-0.2) keeps its sign through s * q - z (-0.0), the reference
+    # dequantises the stored integer code (+0.0); torch.equal treats the two as equal, and so does every consumer
+    want = torch.from_numpy(orc.dequantize(qt, *five)).to(tdt)
+    got = torch.from_numpy(wd.view(np.int16).copy()).view(tdt)
+    assert torch.equal(got, want), "dequantised weights in the weight's dtype"
