@@ -16,18 +16,19 @@
 #include "f32x2.cuh"
 #include "gemm_tf32.cuh"
 #include "tile.cuh"
+#include "rank_update.cuh"
 #include "exact_update_v2.cuh"
 #include <cmath>
 #include <cstdlib>
 
 namespace {
 
-constexpr int R = 32;        // rows per CTA
-constexpr int NT = 256;      // threads per CTA
-constexpr int KP = 16;       // k's per pipeline piece
-constexpr int S = 4;         // pipeline stages
-constexpr int US_FLOATS = KP * 256;
-constexpr int ES_FLOATS = R * KP;
+using rk::R;             // rows per CTA, threads per CTA, k's per pipeline piece, pipeline stages: rank_update.cuh
+using rk::NT;
+using rk::KP;
+using rk::S;
+using rk::US_FLOATS;
+using rk::ES_FLOATS;
 
 struct LayerParams {
     float *W;
@@ -107,87 +108,6 @@ constexpr size_t SMEM_NO_PERM = offsetof(Smem, pc_sc);
 __device__ __forceinline__ int ud_idx(int i, int j) {
     const int l8 = j & 7, sgrp = j >> 3;
     return i * 128 + l8 * 16 + ((((sgrp >> 2) ^ (l8 >> 1)) & 3) << 2) + (sgrp & 3);
-}
-
-// Variants of this loop that were built and measured on B200 and did NOT beat it (profiles/r01_gptq_kernel_notes.md,
-// profiles/microbench/): packed FFMA2 (same FMA rate, 5-6 register reads per issue), a column-per-warp mapping with a
-// k-major E (fewer shared-memory wavefronts, but 4-byte cp.async transposes cost more than they save), a
-// producer/consumer warp split with 8 x 8 register tiles (one warp per SM sub-partition issues an FFMA only every
-// ~1.65 cycles), and a TMA + mbarrier ring.  In isolation the FFMA pattern itself reaches 70 cycles per k (0.91 FFMA
-// per cycle per sub-partition); the pipelined loop runs at ~111.
-// tile(8 rows x 4 cols per thread) -= E[:, kbeg:kend] * U[kbeg:kend, window]; the reference's addmm_ arithmetic.
-// HALF: only the window's columns 128..255 are updated (warps with ch == 1 compute, all warps load).
-template <bool HALF>
-__device__ __forceinline__ void rank_update(float (&w)[8][4], const LayerParams &p, float *__restrict__ Us_base,
-                                            float *__restrict__ Es_base, int r0, int c,
-                                            int kbeg, int kend, int tid, int rg, int ch, int lane) {
-    const int P = (kend - kbeg) / KP;
-    const float *__restrict__ U = p.U;
-    const float *__restrict__ Wg = p.W;
-    const size_t ld = (size_t)p.d_col;
-    auto issue = [&](int pc) {
-        if (pc < P) {
-            const int k0 = kbeg + KP * pc, st = pc % S;
-            float *us = Us_base + st * US_FLOATS;
-            float *es = Es_base + st * ES_FLOATS;
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const int id = tid + NT * m, row = id >> 6, c16 = id & 63;
-                if (!HALF || c16 >= 32) cp_async16(us + row * 256 + 4 * c16, U + (size_t)(k0 + row) * ld + c + 4 * c16);
-            }
-            if (tid < 128) {
-                const int row = tid >> 2, part = tid & 3;
-                const int gr = min(r0 + row, p.d_row - 1);
-                cp_async16(es + row * KP + 4 * part, Wg + (size_t)gr * ld + k0 + 4 * part);
-            }
-        }
-        cp_async_commit();
-    };
-    float acc[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-
-    for (int s = 0; s < S - 1; ++s) issue(s);
-    for (int pc = 0; pc < P; ++pc) {
-        cp_async_wait<S - 2>();
-        __syncthreads();
-        issue(pc + S - 1);
-        if (!HALF || ch == 1) {
-            const float *us = Us_base + (pc % S) * US_FLOATS + ch * 128 + 4 * lane;
-            const float *es = Es_base + (pc % S) * ES_FLOATS + (8 * rg) * KP;
-#pragma unroll
-            for (int kk = 0; kk < KP; kk += 4) {
-                float4 e[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) e[i] = *reinterpret_cast<const float4 *>(es + i * KP + kk);
-#pragma unroll
-                for (int k2 = 0; k2 < 4; ++k2) {
-                    const float4 u = *reinterpret_cast<const float4 *>(us + (kk + k2) * 256);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float ev = k2 == 0 ? e[i].x : k2 == 1 ? e[i].y : k2 == 2 ? e[i].z : e[i].w;
-                        acc[i][0] = __fmaf_rn(ev, u.x, acc[i][0]);
-                        acc[i][1] = __fmaf_rn(ev, u.y, acc[i][1]);
-                        acc[i][2] = __fmaf_rn(ev, u.z, acc[i][2]);
-                        acc[i][3] = __fmaf_rn(ev, u.w, acc[i][3]);
-                    }
-                }
-            }
-        }
-        if ((pc & 7) == 7) {   // end of one earlier 128-column block: w <- w - acc  (gptq.py:270, alpha = -1)
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    w[i][j] = __fsub_rn(w[i][j], acc[i][j]);
-                    acc[i][j] = 0.0f;
-                }
-        }
-    }
-    cp_async_wait<0>();
-    __syncthreads();
 }
 
 // The 128 sequential column steps of one block (gptq.py:229-268), all 8 warps (two per SM sub-partition, so that
@@ -467,28 +387,7 @@ template <int QT> int launch_layer(const LayerParams &p, cudaStream_t st) {
 // kernel leaves most SMs idle while each CTA walks its super-blocks alone, here every SM takes part in every update.
 __global__ void __launch_bounds__(NT, 2) exact_update_kernel(const LayerParams p, const int c) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    float *Us = reinterpret_cast<float *>(smem_raw);
-    float *Es = Us + S * US_FLOATS;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int rg = warp >> 1, ch = warp & 1;
-    const int r0 = blockIdx.y * R;
-    const int cw = c + GQ_QK_K * (1 + blockIdx.x);       // this CTA's window of 256 later columns
-    const size_t ld = (size_t)p.d_col;
-    float w[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int gr = min(r0 + 8 * rg + i, p.d_row - 1);
-        const float4 v = *reinterpret_cast<const float4 *>(p.W + (size_t)gr * ld + cw + ch * 128 + 4 * lane);
-        w[i][0] = v.x; w[i][1] = v.y; w[i][2] = v.z; w[i][3] = v.w;
-    }
-    rank_update<false>(w, p, Us, Es, r0, cw, c, c + GQ_QK_K, tid, rg, ch, lane);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int gr = r0 + 8 * rg + i;
-        if (gr < p.d_row)
-            *reinterpret_cast<float4 *>(p.W + (size_t)gr * ld + cw + ch * 128 + 4 * lane) =
-                make_float4(w[i][0], w[i][1], w[i][2], w[i][3]);
-    }
+    exact_update_body(p, c, smem_raw);
 }
 
 int launch_exact_update(const LayerParams &p, int c, cudaStream_t st) {

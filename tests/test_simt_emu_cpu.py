@@ -62,10 +62,12 @@ def lib_upd(tmp_path_factory):
     return C.CDLL(so)
 
 
+@pytest.mark.parametrize("kernel", ["run_exact_update_v1", "run_exact_update_v2"], ids=["shipped", "v2_experimental"])
 @pytest.mark.parametrize("d_row,d_col,c", [(40, 1024, 256), (33, 768, 0), (64, 1280, 512)])
-def test_exact_update_v2_on_the_emulator(lib_upd, d_row, d_col, c):
-    """gptq_gguf_toolkit_b200/csrc/exact_update_v2.cuh (GQ_UPDATE_V2=1, experimental): the rank-256 trailing update of the exact
-    schedule, W[:, c+256:] <- (W - chain(E[:, c:c+128], U[c:c+128, :])) - chain(E[:, c+128:c+256], U[c+128:c+256, :]) with
+def test_exact_update_on_the_emulator(lib_upd, d_row, d_col, c, kernel):
+    """The SHIPPED trailing-update kernel body (csrc/rank_update.cuh: exact_update_body + rank_update<>, what
+    exact_update_kernel and the left-looking loop of gptq_layer_kernel execute) and the experimental
+    gptq_gguf_toolkit_b200/csrc/exact_update_v2.cuh (GQ_UPDATE_V2=1): the rank-256 trailing update of the exact schedule, W[:, c+256:] <- (W - chain(E[:, c:c+128], U[c:c+128, :])) - chain(E[:, c+128:c+256], U[c+128:c+256, :]) with
     E = W[:, c:c+256], every chain a single-accumulator fp32 FMA chain in ascending k -- bit for bit against a plain
     restatement, ragged row count included; columns left of c+256 and rows must be untouched."""
     import math
@@ -83,7 +85,7 @@ def test_exact_update_v2_on_the_emulator(lib_upd, d_row, d_col, c):
         ref[:, c + 256:] = ref[:, c + 256:] - acc
     got = W.copy()
     p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
-    lib_upd.run_exact_update_v2(p(got, C.c_float), p(U, C.c_float), C.c_int(d_row), C.c_int(d_col), C.c_int(c))
+    getattr(lib_upd, kernel)(p(got, C.c_float), p(U, C.c_float), C.c_int(d_row), C.c_int(d_col), C.c_int(c))
     assert np.array_equal(got[:, :c + 256], W[:, :c + 256]), "columns up to the finished super-block must not change"
     assert np.array_equal(got, ref)
 
