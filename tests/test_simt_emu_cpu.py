@@ -139,3 +139,38 @@ def test_rtn_native_kernel_on_the_emulator(lib_rtn, golden_dir, tname, dtype):
     want = torch.from_numpy(orc.dequantize(qt, *five)).to(tdt)
     got = torch.from_numpy(wd.view(np.int16).copy()).view(tdt)
     assert torch.equal(got, want), "dequantised weights in the weight's dtype"
+
+
+@pytest.mark.parametrize("tname", ["Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"])
+def test_shipped_rtn_kernel_on_the_emulator(lib_rtn, golden_dir, tname):
+    """The SHIPPED RTN kernel body (csrc/rtn_native.cuh: rtn_body, what rtn_kernel / gq_rtn_quantize execute): tile load, fp32
+    search, double quantisation, quantize(), codes, GGUF bytes, dequantised weights -- against the reference golden of the
+    non-block path (tests/golden/rtn.npz, ragged 100-row weight), the oracle's packer and dequantiser."""
+    from oracle import oracle as orc
+    g = np.load(os.path.join(golden_dir, "rtn.npz"))
+    W = np.ascontiguousarray(g["W"], dtype=np.float32)
+    qt = {"Q2_K": 10, "Q3_K": 11, "Q4_K": 12, "Q5_K": 13, "Q6_K": 14}[tname]
+    gs = 32 if tname in ("Q4_K", "Q5_K") else 16
+    ts = {"Q2_K": 84, "Q3_K": 110, "Q4_K": 144, "Q5_K": 176, "Q6_K": 210}[tname]
+    d_row, d_col = W.shape
+    nsb = d_col // 256
+    qw = np.zeros((d_row, d_col), np.uint8)
+    d = np.zeros((d_row, nsb), np.uint16)
+    dmin = np.zeros_like(d)
+    sq = np.zeros((d_row, d_col // gs), np.uint8)
+    zq = np.zeros_like(sq)
+    pk = np.zeros((d_row, nsb * ts), np.uint8)
+    wd = np.zeros((d_row, d_col), np.float32)
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    rc = lib_rtn.run_rtn_fp32(C.c_int(qt), p(W, C.c_float), C.c_int(d_row), C.c_int(d_col), C.c_double(-1.0), C.c_double(0.1), C.c_int(20),
+                              p(qw, C.c_uint8), p(d, C.c_uint16), p(dmin, C.c_uint16), p(sq, C.c_uint8), p(zq, C.c_uint8),
+                              p(pk, C.c_uint8), p(wd, C.c_float))
+    assert rc == 0
+    for k, a in (("qweight", qw), ("d", d), ("sq", sq), ("dmin", dmin), ("zq", zq)):
+        r = g[f"{tname}_ieee_{k}"]
+        r = r.view(np.uint16) if r.dtype == np.float16 else r
+        assert np.array_equal(a.view(np.uint8), r.view(np.uint8).reshape(a.shape[0], -1)), k
+    cd = np.uint8 if tname in ("Q2_K", "Q4_K", "Q5_K") else np.int8
+    five = (qw.view(cd), d.view(np.float16), sq.view(cd), dmin.view(np.float16), zq.view(cd))
+    assert np.array_equal(pk, orc.pack(qt, *five))
+    assert np.array_equal(wd, orc.dequantize(qt, *five))        # value comparison (-0.0 == +0.0, see above)
