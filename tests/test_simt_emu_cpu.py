@@ -1,6 +1,7 @@
 """Kernels written without GPU access, run on the host through a small SIMT emulator (tests/helpers/simt_emu: one fiber per
 CUDA thread, __syncthreads() = barrier between fibers) to catch indexing / algorithm mistakes before they cost GPU minutes.
-Covered: gptq_gguf_toolkit_b200/csrc/chol_diag_v3.cuh, the register-resident diagonal-block kernel (GQ_DIAG_V2=3, experimental)
+Covered: the diagonal-block kernels of gq_prepare -- the shipped chol_diag_v2.cuh and the experimental register-resident
+chol_diag_v3.cuh (GQ_DIAG_V2=3) --
 (128 x 128 Cholesky factor + its inverse + the inverse's transpose, against a double-precision factorisation)."""
 import ctypes as C
 import os
@@ -23,8 +24,19 @@ def lib(tmp_path_factory):
     return C.CDLL(so)
 
 
+@pytest.fixture(scope="module")
+def lib_v2(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu") / "libchol_v2_emu.so")
+    cmd = ["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-I", EMU,
+           "-I", os.path.join(ROOT, "gptq_gguf_toolkit_b200", "csrc"), os.path.join(EMU, "chol_diag_v2_host.cpp"), "-o", so]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-4000:]
+    return C.CDLL(so)
+
+
+@pytest.mark.parametrize("variant", ["v2_shipped", "v3_experimental"])
 @pytest.mark.parametrize("k0", [0, 128])
-def test_chol_diag_v3_on_the_emulator(lib, k0):
+def test_chol_diag_on_the_emulator(lib, lib_v2, k0, variant):
     rng = np.random.default_rng(k0 + 1)
     n, nb = 384, 128
     M = rng.standard_normal((nb, 3 * nb))
@@ -35,7 +47,8 @@ def test_chol_diag_v3_on_the_emulator(lib, k0):
     BinvT = np.full((n, n), 7.0, np.float32)
     flag = np.zeros(1, np.int32)
     p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
-    lib.run_chol_diag_v3(p(A, C.c_float), p(Binv, C.c_float), p(BinvT, C.c_float), C.c_long(n), C.c_int(k0), p(flag, C.c_int))
+    run = lib_v2.run_chol_diag_v2 if variant == "v2_shipped" else lib.run_chol_diag_v3
+    run(p(A, C.c_float), p(Binv, C.c_float), p(BinvT, C.c_float), C.c_long(n), C.c_int(k0), p(flag, C.c_int))
     L = np.linalg.cholesky(H)
     X = np.linalg.inv(L)
     gL = np.tril(A[k0:k0 + nb, k0:k0 + nb].astype(np.float64))
