@@ -30,343 +30,7 @@ using rk::S;
 using rk::US_FLOATS;
 using rk::ES_FLOATS;
 
-struct LayerParams {
-    float *W;
-    const float *U;
-    int d_row, d_col;
-    SearchParams sp;
-    uint8_t *qweight;
-    uint16_t *d;
-    uint8_t *sq;
-    uint16_t *dmin;
-    uint8_t *zq;
-    uint8_t *packed;
-    void *wdeq;
-    int wdeq_dtype;
-    uint32_t *flags;
-    // GQ_MODE_FAST: the kernel handles super-blocks [sb_begin, sb_end) of an already updated W (the rank-k updates
-    // between super-blocks run as tcgen05 GEMMs) and also emits the hi/lo TF32 split of its errors.
-    int sb_begin, sb_end, fast;
-    // skip_bulk: the contributions of all EARLIER super-blocks have already been applied to W by separate launches
-    // (fast mode's tcgen05 GEMMs, or exact_update_kernel in the exact right-looking schedule); the kernel then only
-    // does the search, the column steps and the in-super-block update of [sb_begin, sb_end).
-    int skip_bulk;
-    float *e_hi, *e_lo;     // (rows padded to 128) x 256, only in fast mode
-    f2_t nz2;                  // {-0.0f, -0.0f}, deliberately a run-time value (see f2_mul_nofuse)
-    // static_groups (gptq.py:184-196): d/dmin/sq/zq already hold the scales of EVERY super-block (searched on the
-    // original W), the kernel only reads them.  perm (act_order, gptq.py:209-216; needs static_scales): W and U are in
-    // permuted column order, loop column c is original column perm[c] and uses that column's group (:233-238);
-    // qweight comes out in loop order, the fused pack / dequantised outputs are not available.
-    int static_scales;
-    const int *perm;
-    unsigned long long *clk;   // optional (gq_debug_phase_clocks): 8 per-phase cycle counters summed over CTAs
-};
-
-// phase ids of the optional cycle counters
-enum { PH_RANK = 0, PH_SEARCH, PH_FINAL, PH_SERIAL0, PH_MID, PH_SERIAL1, PH_EMIT, PH_COUNT };
-struct PhaseClock {
-    unsigned long long *out;
-    long long t;
-    __device__ __forceinline__ PhaseClock(unsigned long long *o) : out(o), t(0) {
-        if (out && threadIdx.x == 0) t = clock64();
-    }
-    __device__ __forceinline__ void lap(int ph) {
-        if (out && threadIdx.x == 0) {
-            const long long n = clock64();
-            atomicAdd(out + ph, (unsigned long long)(n - t));
-            t = n;
-        }
-    }
-};
-
-struct __align__(16) Smem {
-    float Wt[R * 256];                       // live super-block tile, later the dequantised values
-    union {
-        struct { float Us[S * US_FLOATS]; float Es[S * ES_FLOATS]; } pipe;
-        float Ud[128 * 128];                 // diagonal block of U during the serial phase
-    } u;
-    float Et[R * 128];                       // errors of the current 128-column block
-    float Wq[R * 128];                       // dequantised values of the current block (copied into Wt when it is done)
-    uint8_t codes[R * 256];
-    float gsc[R * 16];
-    float gzr[R * 16];
-    float dg_b[128];                         // diagonal of the current U block and its checked reciprocal (DivBy)
-    float dg_y[128];
-    float dummy_f[64];                       // sink of the non-owner lanes' stores in the serial phase
-    uint8_t dummy_b[32];
-    RowScales<R> rs;
-    // act_order only -- kept LAST: launches without a permutation allocate the struct up to here (SMEM_NO_PERM)
-    float pc_sc[R * 128];                    // per (row, column of the block) scale, zero, checked 1/scale
-    float pc_zz[R * 128];
-    float pc_y[R * 128];
-};
-constexpr size_t SMEM_NO_PERM = offsetof(Smem, pc_sc);
-
-// Shared-memory layout of the (128 x 128) diagonal block of U for the serial phase: in row i the 16 values a
-// lane (l8 = j & 7) needs -- columns j = 8s + l8 -- are contiguous (64 B), 16-byte chunks XOR-swizzled by (l8 >> 1) & 3
-// so that the eight lanes of a row group read eight different bank groups with one LDS.128 each.
-__device__ __forceinline__ int ud_idx(int i, int j) {
-    const int l8 = j & 7, sgrp = j >> 3;
-    return i * 128 + l8 * 16 + ((((sgrp >> 2) ^ (l8 >> 1)) & 3) << 2) + (sgrp & 3);
-}
-
-// The 128 sequential column steps of one block (gptq.py:229-268), all 8 warps (two per SM sub-partition, so that
-// one warp's off-chain work fills the other's dependency stalls).  8 lanes per row; lane l8 holds the block's columns
-// {8s + l8}, s = 0..15, as 8 packed pairs.  Column i = 8s+q is broadcast from its owner, every lane of the row redoes
-// the (cheap) quantise/err arithmetic, then updates its not-yet-consumed columns:  w -= fl(err * U[i, j])
-// (two roundings: f2_mul_nofuse then sub.rn.f32x2).
-// The two divisions of the dependent chain -- (x + z) / max(s, eps) and (x - w_q) / U[i,i] -- use reciprocals prepared
-// off the chain (DivBy, f32x2.cuh).  SAFE = false: branch-free (DivBy::div_fast, stores through a select-ed pointer);
-// returns true if some quotient was outside the range in which div_fast is proven exact -- the caller then reruns the
-// block with SAFE = true (IEEE fallback inside DivBy::div).  The block's initial values are read from Wt, its
-// dequantised values go to `Wq` (a separate buffer), so a rerun starts from unchanged inputs.
-template <int QT, bool SAFE>
-__device__ __noinline__ bool serial_block_impl(Smem &sm, int blk, int warp, int lane, f2_t nz2, bool per_col) {
-    constexpr int GS = Fmt<QT>::GS;
-    const float lo = (float)Fmt<QT>::QMIN, hi = (float)Fmt<QT>::QMAX;
-    const int l8 = lane & 7, srow = warp * 4 + (lane >> 3);
-    f2_t pr[8];
-#pragma unroll
-    for (int m = 0; m < 8; ++m)
-        pr[m] = f2_pack(sm.Wt[wt_idx(srow, blk * 128 + 16 * m + l8)], sm.Wt[wt_idx(srow, blk * 128 + 16 * m + 8 + l8)]);
-    const float d = sm.rs.d[srow], dm = sm.rs.dm[srow];
-    const float *Ud = sm.u.Ud + l8 * 16;
-    const int sw = (l8 >> 1) & 3;
-    float *et = sm.Et + srow * 128, *wqo = sm.Wq + srow * 128;
-    uint8_t *cd = sm.codes + srow * 256 + blk * 128;
-    float sc = 0.0f, zz = 0.0f;
-    DivBy ds = DivBy::make(1.0f);
-    bool bad = false;
-#pragma unroll
-    for (int s = 0; s < 16; ++s) {
-        if (!per_col && (8 * s) % GS == 0) {
-            const int g = (blk * 128 + 8 * s) / GS;
-            sc = __fmul_rn(d, kq_code_to_f<QT>(sm.rs.sq[srow][g]));
-            zz = __fmul_rn(dm, kq_code_to_f<QT>(sm.rs.zq[srow][g]));
-            ds = DivBy::make(fmaxf(sc, GQ_EPS));
-        }
-#pragma unroll 1
-        for (int q = 0; q < 8; ++q) {
-            const int i = 8 * s + q;
-            // loads that do not depend on the chain first: U[i, my columns], the diagonal's reciprocal
-            const float4 *urow = reinterpret_cast<const float4 *>(Ud + i * 128);
-            float4 u[4];
-#pragma unroll
-            for (int c4 = s >> 2; c4 < 4; ++c4) u[c4] = urow[c4 ^ sw];
-            DivBy du;
-            du.b = sm.dg_b[i];
-            du.y = sm.dg_y[i];
-            if (per_col) {          // act_order: every column has its own group (gptq.py:233-238)
-                sc = sm.pc_sc[srow * 128 + i];
-                zz = sm.pc_zz[srow * 128 + i];
-                ds.b = fmaxf(sc, GQ_EPS);
-                ds.y = sm.pc_y[srow * 128 + i];
-            }
-            float plo, phi;
-            f2_unpack(pr[s >> 1], plo, phi);
-            const float x = __shfl_sync(0xffffffffu, (s & 1) ? phi : plo, q, 8);
-            const float t = __fadd_rn(x, zz);
-            const float qv = clampf(rintf(SAFE ? ds.div(t) : ds.div_fast(t, bad)), lo, hi);   // :247-254 (kq_quant)
-            const float wq = kq_dequant(qv, sc, zz);                                          // :255-261
-            const float num = __fsub_rn(x, wq);
-            const float err = SAFE ? du.div(num) : du.div_fast(num, bad);                     // :264
-            const f2_t e2 = f2_pack(err, err);
-#pragma unroll
-            for (int c4 = s >> 2; c4 < 4; ++c4) {                                             // :267
-                if (2 * c4 >= (s >> 1)) pr[2 * c4] = f2_sub(pr[2 * c4], f2_mul_nofuse(e2, f2_pack(u[c4].x, u[c4].y), nz2));
-                pr[2 * c4 + 1] = f2_sub(pr[2 * c4 + 1], f2_mul_nofuse(e2, f2_pack(u[c4].z, u[c4].w), nz2));
-            }
-            // outputs of column i: the owner lane stores, the others write to a per-lane dummy slot (no branch)
-            const bool own = (l8 == q);
-            float *ep = own ? et + i : sm.dummy_f + lane;
-            float *wp = own ? wqo + i : sm.dummy_f + 32 + lane;
-            uint8_t *cp = own ? cd + i : sm.dummy_b + lane;
-            *ep = err;                                                                        // :268
-            *wp = wq;                                                                         // :266
-            *cp = (uint8_t)(int8_t)(int)qv;                                                   // :263
-        }
-    }
-    return bad;
-}
-
-template <int QT>
-__device__ __forceinline__ void serial_block(Smem &sm, int blk, int warp, int lane, f2_t nz2, bool per_col) {
-    const bool bad = serial_block_impl<QT, false>(sm, blk, warp, lane, nz2, per_col);
-    if (__any_sync(0xffffffffu, bad)) serial_block_impl<QT, true>(sm, blk, warp, lane, nz2, per_col);   // rare: exact IEEE divisions
-    __syncwarp();
-    // the block's dequantised values replace the consumed columns of the tile (this warp's 4 rows)
-    const int srow = warp * 4 + (lane >> 3), l8 = lane & 7;
-#pragma unroll
-    for (int s = 0; s < 16; ++s) sm.Wt[wt_idx(srow, blk * 128 + 8 * s + l8)] = sm.Wq[srow * 128 + 8 * s + l8];
-}
-
-// (A register-capped build of this kernel for the panel launches of the right-looking schedule -- __launch_bounds__(256, 2),
-// 128 registers, two co-resident CTAs per SM -- was measured on B200 and was 3-5 % SLOWER at every shape: the K-quant search
-// of the 32-weight-group types spills, and the column steps lose the registers that keep their loads ahead of the chain.)
-template <int QT>
-__global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-    constexpr int GS = Fmt<QT>::GS, GPR = GQ_QK_K / GS;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int rg = warp >> 1, ch = warp & 1;            // rank-update mapping: rows 8rg..8rg+7, cols ch*128+4*lane..
-    const int r0 = blockIdx.x * R;
-    const int nsb = p.d_col / GQ_QK_K, ng = p.d_col / GS;
-    const size_t ld = (size_t)p.d_col;
-
-    // Diagonal (128 x 128) block of U -> shared memory in the serial phase's permuted layout (ud_idx).  Row i only
-    // needs its columns j >= 32*(i/32) (the lanes read whole 16-byte chunks = 32-column spans at and right of the diagonal).
-    auto load_Ud = [&](int c1) {
-        for (int id = tid; id < 128 * 128; id += NT) {
-            const int i = id >> 7, j = id & 127;
-            if (j >= (i & ~31)) cp_async4(sm.u.Ud + ud_idx(i, j), p.U + (size_t)(c1 + i) * ld + c1 + j);
-        }
-        cp_async_commit();
-    };
-    auto diag_recip = [&]() {      // after Ud has landed: checked reciprocals of the diagonal (off the dependent chain)
-        if (tid < 128) {
-            const DivBy dv = DivBy::make(sm.u.Ud[ud_idx(tid, tid)]);
-            sm.dg_b[tid] = dv.b;
-            sm.dg_y[tid] = dv.y;
-        }
-    };
-    auto store_E = [&](int c1) {   // errors of the block replace the consumed columns of W
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const int id = tid + NT * m, row = id >> 5, c4 = id & 31;
-            if (r0 + row < p.d_row) {
-                const float4 e = *reinterpret_cast<const float4 *>(sm.Et + row * 128 + 4 * c4);
-                *reinterpret_cast<float4 *>(p.W + (size_t)(r0 + row) * ld + c1 + 4 * c4) = e;
-                if (p.fast) {      // operands of the next tcgen05 rank-256 update: hi = TF32 part, lo = remainder
-                    float4 h, l;
-                    h.x = __uint_as_float(__float_as_uint(e.x) & 0xFFFFE000u); l.x = __fsub_rn(e.x, h.x);
-                    h.y = __uint_as_float(__float_as_uint(e.y) & 0xFFFFE000u); l.y = __fsub_rn(e.y, h.y);
-                    h.z = __uint_as_float(__float_as_uint(e.z) & 0xFFFFE000u); l.z = __fsub_rn(e.z, h.z);
-                    h.w = __uint_as_float(__float_as_uint(e.w) & 0xFFFFE000u); l.w = __fsub_rn(e.w, h.w);
-                    const size_t o = (size_t)(r0 + row) * 256 + (c1 & 255) + 4 * c4;
-                    *reinterpret_cast<float4 *>(p.e_hi + o) = h;
-                    *reinterpret_cast<float4 *>(p.e_lo + o) = l;
-                }
-            }
-        }
-    };
-    auto per_column_tables = [&](int c1) {      // act_order: scale / zero / checked reciprocal of every (row, column) of a block
-        for (int id = tid; id < R * 128; id += NT) {
-            const int row = id >> 7, i = id & 127;
-            const int ocol = p.perm[c1 + i];
-            const size_t gr = (size_t)min(r0 + row, p.d_row - 1);
-            const float dd = __half2float(__ushort_as_half(p.d[gr * nsb + (ocol >> 8)]));
-            const float dm = __half2float(__ushort_as_half(p.dmin[gr * nsb + (ocol >> 8)]));
-            const float sc = __fmul_rn(dd, kq_code_to_f<QT>(p.sq[gr * ng + ocol / GS]));
-            const float zz = __fmul_rn(dm, kq_code_to_f<QT>(p.zq[gr * ng + ocol / GS]));
-            sm.pc_sc[id] = sc;
-            sm.pc_zz[id] = zz;
-            sm.pc_y[id] = DivBy::make(fmaxf(sc, GQ_EPS)).y;
-        }
-    };
-    const bool per_col = p.perm != nullptr;
-    PhaseClock pc(p.clk);
-    for (int sb = p.sb_begin; sb < p.sb_end; ++sb) {
-        const int c = sb * GQ_QK_K;
-        float w[8][4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int gr = min(r0 + 8 * rg + i, p.d_row - 1);
-            const float4 v = *reinterpret_cast<const float4 *>(p.W + (size_t)gr * ld + c + ch * 128 + 4 * lane);
-            w[i][0] = v.x; w[i][1] = v.y; w[i][2] = v.z; w[i][3] = v.w;
-        }
-        __syncthreads();   // previous super-block is completely done with the shared buffers
-        rank_update<false>(w, p, sm.u.pipe.Us, sm.u.pipe.Es, r0, c, 0, p.skip_bulk ? 0 : c, tid, rg, ch, lane);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4 *>(sm.Wt + wt_idx4(8 * rg + i, ch * 32 + lane)) =
-                make_float4(w[i][0], w[i][1], w[i][2], w[i][3]);
-        __syncthreads();
-        pc.lap(PH_RANK);
-
-        // scale / min search on the live tile (gptq.py:240-245 -> quant_utils.py:90-145); U's diagonal
-        // block for the first 128 columns streams in underneath it.
-        load_Ud(c);
-        if (!p.static_scales) {
-            uint32_t vmask = 0, amask = 0;
-            tile_search<QT, R, NT>(sm.Wt, sm.gsc, sm.gzr, p.sp, vmask, amask);
-            publish_flags(p.flags ? p.flags + 2 * sb : nullptr, vmask, amask);
-        }
-        cp_async_wait<0>();
-        __syncthreads();
-        pc.lap(PH_SEARCH);
-        diag_recip();
-        if (tid >= 128 && tid < 128 + R) {
-            const int row = tid - 128;
-            const size_t gr = (size_t)min(r0 + row, p.d_row - 1);
-            if (!p.static_scales) {
-                tile_finalize_row<QT, R>(row, sm.gsc, sm.gzr, sm.rs);
-                if (r0 + row < p.d_row) {
-                    p.d[gr * nsb + sb] = sm.rs.dbits[row];
-                    p.dmin[gr * nsb + sb] = sm.rs.dmbits[row];
-#pragma unroll
-                    for (int g = 0; g < GPR; ++g) {
-                        p.sq[gr * ng + sb * GPR + g] = sm.rs.sq[row][g];
-                        p.zq[gr * ng + sb * GPR + g] = sm.rs.zq[row][g];
-                    }
-                }
-            } else if (p.perm == nullptr) {       // static_groups: this super-block's scales were searched up front
-                sm.rs.dbits[row] = p.d[gr * nsb + sb];
-                sm.rs.dmbits[row] = p.dmin[gr * nsb + sb];
-                sm.rs.d[row] = __half2float(__ushort_as_half(sm.rs.dbits[row]));
-                sm.rs.dm[row] = __half2float(__ushort_as_half(sm.rs.dmbits[row]));
-#pragma unroll
-                for (int g = 0; g < GPR; ++g) {
-                    sm.rs.sq[row][g] = p.sq[gr * ng + sb * GPR + g];
-                    sm.rs.zq[row][g] = p.zq[gr * ng + sb * GPR + g];
-                }
-            }
-        }
-        if (p.perm != nullptr) per_column_tables(c);
-        __syncthreads();
-        pc.lap(PH_FINAL);
-
-        serial_block<QT>(sm, 0, warp, lane, p.nz2, per_col);
-        __syncthreads();
-        pc.lap(PH_SERIAL0);
-        store_E(c);
-        __syncthreads();   // E of block 0 visible to the whole CTA; Ud is free again
-
-        // the first block's rank-k update onto the super-block's second half
-        if (ch == 1) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 v = *reinterpret_cast<const float4 *>(sm.Wt + wt_idx4(8 * rg + i, 32 + lane));
-                w[i][0] = v.x; w[i][1] = v.y; w[i][2] = v.z; w[i][3] = v.w;
-            }
-        }
-        rank_update<true>(w, p, sm.u.pipe.Us, sm.u.pipe.Es, r0, c, c, c + 128, tid, rg, ch, lane);
-        if (ch == 1) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                *reinterpret_cast<float4 *>(sm.Wt + wt_idx4(8 * rg + i, 32 + lane)) =
-                    make_float4(w[i][0], w[i][1], w[i][2], w[i][3]);
-        }
-        load_Ud(c + 128);
-        cp_async_wait<0>();
-        __syncthreads();
-        diag_recip();
-        if (per_col) per_column_tables(c + 128);
-        __syncthreads();
-        pc.lap(PH_MID);
-
-        serial_block<QT>(sm, 1, warp, lane, p.nz2, per_col);
-        __syncthreads();
-        pc.lap(PH_SERIAL1);
-        store_E(c + 128);
-
-        // outputs of the finished super-block: codes, GGUF bytes, dequantised weights
-        tile_emit<QT, R, NT>(sm.Wt, sm.codes, sm.rs, r0, p.d_row, ld, c, sb, nsb, p.qweight, p.packed, p.wdeq,
-                             p.wdeq_dtype);
-        pc.lap(PH_EMIT);
-    }
-}
+#include "gptq_layer_kernel.cuh"      // LayerParams, Smem, serial_block<>, gptq_layer_kernel<QT>
 
 template <int QT> int launch_layer(const LayerParams &p, cudaStream_t st) {
     const int grid = (p.d_row + R - 1) / R;

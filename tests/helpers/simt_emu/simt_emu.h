@@ -5,7 +5,8 @@
 //     are NOT detected -- this finds deterministic mistakes (wrong index, missing barrier that matters in thread order,
 //     wrong formula), nothing more;
 //   * shared memory: the kernel's `extern __shared__ ... raw[]` binds to the array the harness defines.
-// Not supported: warp shuffles / votes, atomics, cp.async, tensor cores, clusters.
+//   * warp shuffles (float), votes and __syncwarp() are warp-level barriers + an exchange buffer.
+// Not supported: tensor cores, clusters, real atomics (harnesses provide what a kernel needs), timing.
 #pragma once
 #include <ucontext.h>
 
@@ -36,29 +37,83 @@ static inline float4 make_float4(float x, float y, float z, float w) { return fl
 #define __restrict__
 
 namespace simt {
+// Scheduler: fibers run round-robin; a fiber that reaches a barrier (block-wide or warp-wide) registers its arrival and is
+// only resumed past it when every live thread of the block / of its warp has arrived (generation counters), so barriers of
+// different kinds and warp-divergent code (one warp shuffling while another waits at __syncthreads) keep CUDA's semantics.
 struct Fiber { ucontext_t ctx; std::vector<char> stack; bool done = false; };
 inline dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
 inline ucontext_t g_sched;
 inline std::vector<Fiber> *g_fibers = nullptr;
-inline int g_current = -1;
+inline int g_current = -1, g_nt = 0;
 inline std::function<void()> *g_body = nullptr;
+inline int g_live = 0;                                  // threads of the block that have not returned yet
+inline int g_block_arrived = 0;
+inline unsigned long g_block_gen = 0;
+inline std::vector<int> g_warp_arrived, g_warp_live;
+inline std::vector<unsigned long> g_warp_gen;
+inline std::vector<uint32_t> g_xchg;                    // one 32-bit slot per thread for shuffles / votes
+
+inline void yield_to_scheduler() { swapcontext(&(*g_fibers)[g_current].ctx, &g_sched); }
 inline void trampoline() {
     (*g_body)();
+    const int w = g_current >> 5;
     (*g_fibers)[g_current].done = true;
-    swapcontext(&(*g_fibers)[g_current].ctx, &g_sched);
+    --g_live;
+    --g_warp_live[w];
+    // a thread that leaves must not keep others waiting forever: leaving counts as "no longer expected" at barriers
+    if (g_live > 0 && g_block_arrived == g_live) { g_block_arrived = 0; ++g_block_gen; }
+    if (g_warp_live[w] > 0 && g_warp_arrived[w] == g_warp_live[w]) { g_warp_arrived[w] = 0; ++g_warp_gen[w]; }
+    yield_to_scheduler();
 }
-inline void syncthreads() { swapcontext(&(*g_fibers)[g_current].ctx, &g_sched); }
+inline void syncthreads() {
+    const unsigned long gen = g_block_gen;
+    if (++g_block_arrived == g_live) { g_block_arrived = 0; ++g_block_gen; return; }
+    while (g_block_gen == gen) yield_to_scheduler();
+}
+inline void syncwarp() {
+    const int w = g_current >> 5;
+    const unsigned long gen = g_warp_gen[w];
+    if (++g_warp_arrived[w] == g_warp_live[w]) { g_warp_arrived[w] = 0; ++g_warp_gen[w]; return; }
+    while (g_warp_gen[w] == gen) yield_to_scheduler();
+}
+// warp exchange: every lane publishes a 32-bit value, then reads what it needs (two warp barriers)
+template <class F> inline uint32_t warp_exchange(uint32_t mine, F reader) {
+    g_xchg[g_current] = mine;
+    syncwarp();
+    const uint32_t r = reader((g_current >> 5) << 5);   // reader gets the index of lane 0 of this warp in g_xchg
+    syncwarp();
+    return r;
+}
+inline float shfl(float v, int src, int width) {
+    uint32_t bits; std::memcpy(&bits, &v, 4);
+    const int lane = g_current & 31;
+    const int from = (lane / width) * width + (src % width);
+    const uint32_t r = warp_exchange(bits, [&](int base) { return g_xchg[base + from]; });
+    float out; std::memcpy(&out, &r, 4); return out;
+}
+inline bool any(bool pred) {
+    return warp_exchange(pred ? 1u : 0u, [&](int base) { uint32_t o = 0; for (int l = 0; l < 32 && base + l < g_nt; ++l) o |= g_xchg[base + l]; return o; }) != 0;
+}
+inline uint32_t reduce_or(uint32_t v) {
+    return warp_exchange(v, [&](int base) { uint32_t o = 0; for (int l = 0; l < 32 && base + l < g_nt; ++l) o |= g_xchg[base + l]; return o; });
+}
 
 // Runs body() once per thread of every block of the grid; blocks one after the other.
 inline void launch(dim3 grid, dim3 block, std::function<void()> body, size_t stack_bytes = 256 * 1024) {
     g_gridDim = grid; g_blockDim = block; g_body = &body;
     const int nt = (int)(block.x * block.y * block.z);
+    g_nt = nt;
     for (unsigned bz = 0; bz < grid.z; ++bz)
         for (unsigned by = 0; by < grid.y; ++by)
             for (unsigned bx = 0; bx < grid.x; ++bx) {
                 g_blockIdx = dim3(bx, by, bz);
                 std::vector<Fiber> fibers(nt);
                 g_fibers = &fibers;
+                g_live = nt; g_block_arrived = 0; g_block_gen = 0;
+                const int nw = (nt + 31) / 32;
+                g_warp_arrived.assign(nw, 0); g_warp_gen.assign(nw, 0); g_warp_live.assign(nw, 0);
+                for (int t = 0; t < nt; ++t) ++g_warp_live[t >> 5];
+                g_xchg.assign(nt, 0);
                 for (int t = 0; t < nt; ++t) {
                     fibers[t].stack.resize(stack_bytes);
                     getcontext(&fibers[t].ctx);
@@ -67,22 +122,24 @@ inline void launch(dim3 grid, dim3 block, std::function<void()> body, size_t sta
                     fibers[t].ctx.uc_link = &g_sched;
                     makecontext(&fibers[t].ctx, trampoline, 0);
                 }
-                int remaining = nt;
-                while (remaining > 0) {          // one pass = every live fiber runs up to its next barrier (or to the end)
-                    int finished_now = 0, live = 0;
+                unsigned long idle_passes = 0, last_progress = ~0ul;
+                while (g_live > 0) {
+                    const unsigned long progress = g_block_gen * 1000003ul + (unsigned long)g_live;
+                    unsigned long wsum = 0;
+                    for (auto g : g_warp_gen) wsum += g;
+                    const unsigned long state = progress ^ (wsum << 20);
+                    idle_passes = (state == last_progress) ? idle_passes + 1 : 0;
+                    last_progress = state;
+                    if (idle_passes > 4) {
+                        std::fprintf(stderr, "simt_emu: deadlock -- %d live threads, %d at the block barrier\n", g_live, g_block_arrived);
+                        std::abort();
+                    }
                     for (int t = 0; t < nt; ++t) {
                         if (fibers[t].done) continue;
-                        ++live;
                         g_current = t;
                         g_threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
                         swapcontext(&g_sched, &fibers[t].ctx);
-                        if (fibers[t].done) ++finished_now;
                     }
-                    if (finished_now != 0 && finished_now != live) {
-                        std::fprintf(stderr, "simt_emu: %d of %d threads left the kernel while the others wait at a barrier\n", finished_now, live);
-                        std::abort();
-                    }
-                    remaining -= finished_now;
                 }
             }
 }
@@ -93,3 +150,7 @@ inline void launch(dim3 grid, dim3 block, std::function<void()> body, size_t sta
 #define blockDim (simt::g_blockDim)
 #define gridDim (simt::g_gridDim)
 #define __syncthreads() simt::syncthreads()
+#define __syncwarp() simt::syncwarp()
+#define __shfl_sync(mask, v, src, width) simt::shfl((v), (src), (width))
+#define __any_sync(mask, pred) simt::any(pred)
+#define __noinline__
