@@ -6,11 +6,25 @@
 // to the scalar `_rn` intrinsics.  Everything here keeps the library's numerical contract (-fmad=false, every
 // rounding explicit): f2_fma == two __fmaf_rn, f2_mul_nofuse == two __fmul_rn, f2_add/f2_sub == two __fadd_rn/__fsub_rn.
 #pragma once
+#ifndef SIMT_EMU
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 typedef unsigned long long f2_t;    // two fp32 in one 64-bit register pair: {lo, hi}
 
+#ifdef SIMT_EMU      // the CPU suite runs the kernels on an emulator (tests/helpers/simt_emu): same element-wise IEEE operations
+#define F2_NEG_ZERO2 0x8000000080000000ull
+static inline f2_t f2_pack(float lo, float hi) { uint32_t a, b; memcpy(&a, &lo, 4); memcpy(&b, &hi, 4); return (f2_t)a | ((f2_t)b << 32); }
+static inline void f2_unpack(f2_t v, float &lo, float &hi) { uint32_t a = (uint32_t)v, b = (uint32_t)(v >> 32); memcpy(&lo, &a, 4); memcpy(&hi, &b, 4); }
+static inline f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
+    float al, ah, bl, bh, cl, ch; f2_unpack(a, al, ah); f2_unpack(b, bl, bh); f2_unpack(c, cl, ch);
+    return f2_pack(fmaf(al, bl, cl), fmaf(ah, bh, ch));
+}
+static inline f2_t f2_mul_nofuse(f2_t a, f2_t b, f2_t nz) { return f2_fma(a, b, nz); }
+static inline f2_t f2_add(f2_t a, f2_t b) { float al, ah, bl, bh; f2_unpack(a, al, ah); f2_unpack(b, bl, bh); return f2_pack(al + bl, ah + bh); }
+static inline f2_t f2_sub(f2_t a, f2_t b) { float al, ah, bl, bh; f2_unpack(a, al, ah); f2_unpack(b, bl, bh); return f2_pack(al - bl, ah - bh); }
+#else
 __device__ __forceinline__ f2_t f2_pack(float lo, float hi) {
     f2_t r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -45,6 +59,8 @@ __device__ __forceinline__ f2_t f2_sub(f2_t a, f2_t b) {
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+
+#endif  // SIMT_EMU
 
 // ---------------------------------------------------------------------------------------------
 // Exact a / b with the divisor's reciprocal hoisted out of a dependent chain.

@@ -187,3 +187,54 @@ def test_shipped_rtn_kernel_on_the_emulator(lib_rtn, golden_dir, tname):
     five = (qw.view(cd), d.view(np.float16), sq.view(cd), dmin.view(np.float16), zq.view(cd))
     assert np.array_equal(pk, orc.pack(qt, *five))
     assert np.array_equal(wd, orc.dequantize(qt, *five))        # value comparison (-0.0 == +0.0, see above)
+
+
+# ------------------------------------------------------------------------------------------------
+# the SHIPPED fused column-loop kernel against the reference goldens (B1), on the emulator
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def lib_layer(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu") / "libgptq_layer_emu.so")
+    cmd = ["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-I", EMU,
+           "-I", os.path.join(ROOT, "tests", "helpers", "host_shim"), "-I", os.path.join(ROOT, "gptq_gguf_toolkit_b200", "csrc"),
+           os.path.join(EMU, "gptq_layer_host.cpp"), "-o", so]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-4000:]
+    return C.CDLL(so)
+
+
+@pytest.mark.parametrize("schedule", ["left_looking", "right_looking"])
+@pytest.mark.parametrize("case", ["b1_a.npz", "b1_b.npz"])
+@pytest.mark.parametrize("tname", ["Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"])
+def test_shipped_column_loop_kernel_matches_reference_golden(lib_layer, golden_dir, tname, case, schedule):
+    """gptq_gguf_toolkit_b200/csrc/gptq_layer_kernel.cuh (gptq_layer_kernel<QT>: per-256 scale / min search, the 256 dependent
+    column steps with their warp shuffles and exact divisions, in-super-block and left-looking rank-k updates, GGUF bit-pack,
+    dequantised write-back) and rank_update.cuh (the trailing update of the right-looking schedule) -- the source that ships in
+    libgq -- executed on the SIMT emulator on the reference's own B1 goldens (gptq.py:146-295 on CPU, ragged row counts):
+    codes, the four scale tensors, the packed GGUF bytes and the dequantised weights must be bit-identical, in both schedules."""
+    g = np.load(os.path.join(golden_dir, case))
+    assert int(g["block_size"]) == 128
+    W = np.ascontiguousarray(g["W"], dtype=np.float32).copy()
+    U = np.ascontiguousarray(g["U_colmajor_T"].T, dtype=np.float32)      # the reference's U is column-major
+    qt = {"Q2_K": 10, "Q3_K": 11, "Q4_K": 12, "Q5_K": 13, "Q6_K": 14}[tname]
+    gs = 32 if tname in ("Q4_K", "Q5_K") else 16
+    ts = {"Q2_K": 84, "Q3_K": 110, "Q4_K": 144, "Q5_K": 176, "Q6_K": 210}[tname]
+    d_row, d_col = W.shape
+    nsb = d_col // 256
+    qw = np.zeros((d_row, d_col), np.uint8)
+    d = np.zeros((d_row, nsb), np.uint16)
+    dmin = np.zeros_like(d)
+    sq = np.zeros((d_row, d_col // gs), np.uint8)
+    zq = np.zeros_like(sq)
+    pk = np.zeros((d_row, nsb * ts), np.uint8)
+    wd = np.zeros((d_row, d_col), np.float32)
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    rc = lib_layer.run_gptq_layer(C.c_int(qt), C.c_int(1 if schedule == "right_looking" else 0), p(W, C.c_float), p(U, C.c_float),
+                                  C.c_int(d_row), C.c_int(d_col), C.c_double(-1.0), C.c_double(0.1), C.c_int(20), p(qw, C.c_uint8),
+                                  p(d, C.c_uint16), p(sq, C.c_uint8), p(dmin, C.c_uint16), p(zq, C.c_uint8), p(pk, C.c_uint8), p(wd, C.c_float))
+    assert rc == 0
+    for k, a in (("qweight", qw), ("d", d), ("sq", sq), ("dmin", dmin), ("zq", zq), ("packed", pk)):
+        r = g[f"{tname}_ieee_{k}"]
+        r = r.view(np.uint16) if r.dtype == np.float16 else r
+        assert np.array_equal(a.view(np.uint8), r.view(np.uint8).reshape(a.shape[0], -1)), f"{k} differs from the reference"
+    assert np.array_equal(wd, g[f"{tname}_ieee_dequant"]), "dequantised weights"
