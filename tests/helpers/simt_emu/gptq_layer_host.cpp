@@ -35,6 +35,7 @@ template <int N> static inline void cp_async_wait() {
 #include "f32x2.cuh"
 #include "tile.cuh"
 #include "rank_update.cuh"
+#include "rtn_native.cuh"
 
 namespace {
 alignas(16) uint8_t smem_raw[224 * 1024];      // the kernel's `extern __shared__ ... smem_raw[]` (declared inside this namespace)
@@ -60,17 +61,60 @@ template <int QT> void run(LayerParams p, int right_looking) {
 }
 }  // namespace
 
-// W (d_row x d_col fp32, clobbered with the propagated errors), U row-major upper; outputs like gq_gptq_quantize (fp32 wdeq)
+// ---- static_groups (gptq.py:184-196): all scales up front = the RTN search over the whole matrix (gq_search_all_superblocks)
+namespace {
+struct RtnParams {
+    const void *W; int w_dtype; long ld_in; int d_row, nsb; SearchParams sp;
+    uint16_t *d, *dmin; long d_stride; uint8_t *sq, *zq; long sq_stride;
+    uint8_t *qweight; uint8_t *packed; void *wdeq; int wdeq_dtype; uint32_t *flags;
+};
+struct alignas(16) RtnSmem { float Wt[32 * 256]; uint8_t codes[32 * 256]; float gsc[32 * 16]; float gzr[32 * 16]; RowScales<32> rs; };
+RtnSmem g_rtn_sm;
+template <int QT> void search_all(const RtnParams &p) {
+    simt::launch(dim3((p.d_row + 31) / 32, p.nsb), dim3(256), [&]() { rtn_body<QT, 32, 256, RtnParams, RtnSmem>(p, g_rtn_sm); });
+}
+}  // namespace
+extern "C" int run_search_all(int qtype, const float *W, int d_row, int d_col, double rmin, double rdelta, int nstep, uint16_t *d,
+                              uint16_t *dmin, uint8_t *sq, uint8_t *zq) {
+    const int bits = qtype == GQ_Q2_K ? 2 : qtype == GQ_Q3_K ? 3 : qtype == GQ_Q4_K ? 4 : qtype == GQ_Q5_K ? 5 : 6;
+    const int gs = (qtype == GQ_Q4_K || qtype == GQ_Q5_K) ? 32 : 16;
+    RtnParams p;
+    p.W = W; p.w_dtype = GQ_F32; p.ld_in = d_col; p.d_row = d_row; p.nsb = d_col / 256;
+    p.sp.nstep = nstep;
+    for (int i = 0; i <= nstep && i < 64; ++i) p.sp.num[i] = (float)(rmin + rdelta * (double)i + (double)((1 << bits) - 1));
+    p.d = d; p.dmin = dmin; p.d_stride = p.nsb; p.sq = sq; p.zq = zq; p.sq_stride = d_col / gs;
+    p.qweight = nullptr; p.packed = nullptr; p.wdeq = nullptr; p.wdeq_dtype = GQ_F32; p.flags = nullptr;
+    switch (qtype) {
+    case GQ_Q2_K: search_all<GQ_Q2_K>(p); return 0;
+    case GQ_Q3_K: search_all<GQ_Q3_K>(p); return 0;
+    case GQ_Q4_K: search_all<GQ_Q4_K>(p); return 0;
+    case GQ_Q5_K: search_all<GQ_Q5_K>(p); return 0;
+    case GQ_Q6_K: search_all<GQ_Q6_K>(p); return 0;
+    }
+    return -1;
+}
+
+// W (d_row x d_col fp32, clobbered with the propagated errors), U row-major upper; outputs like gq_gptq_quantize_ex (fp32 wdeq).
+// static_scales != 0: d / dmin / sq / zq hold the scales on entry; perm (may be null): act_order, W and U in permuted order,
+// qweight comes out in loop order, packed / wdeq must be null then.
+extern "C" int run_gptq_layer_ex(int qtype, int right_looking, float *W, const float *U, int d_row, int d_col, double rmin, double rdelta,
+                                 int nstep, int static_scales, const int *perm, uint8_t *qweight, uint16_t *d, uint8_t *sq, uint16_t *dmin,
+                                 uint8_t *zq, uint8_t *packed, float *wdeq);
 extern "C" int run_gptq_layer(int qtype, int right_looking, float *W, const float *U, int d_row, int d_col, double rmin, double rdelta,
                               int nstep, uint8_t *qweight, uint16_t *d, uint8_t *sq, uint16_t *dmin, uint8_t *zq, uint8_t *packed,
                               float *wdeq) {
+    return run_gptq_layer_ex(qtype, right_looking, W, U, d_row, d_col, rmin, rdelta, nstep, 0, nullptr, qweight, d, sq, dmin, zq, packed, wdeq);
+}
+extern "C" int run_gptq_layer_ex(int qtype, int right_looking, float *W, const float *U, int d_row, int d_col, double rmin, double rdelta,
+                                 int nstep, int static_scales, const int *perm, uint8_t *qweight, uint16_t *d, uint8_t *sq, uint16_t *dmin,
+                                 uint8_t *zq, uint8_t *packed, float *wdeq) {
     const int bits = qtype == GQ_Q2_K ? 2 : qtype == GQ_Q3_K ? 3 : qtype == GQ_Q4_K ? 4 : qtype == GQ_Q5_K ? 5 : 6;
     LayerParams p;
     p.W = W; p.U = U; p.d_row = d_row; p.d_col = d_col;
     p.sp.nstep = nstep;
     for (int i = 0; i <= nstep && i < 64; ++i) p.sp.num[i] = (float)(rmin + rdelta * (double)i + (double)((1 << bits) - 1));
     p.qweight = qweight; p.d = d; p.sq = sq; p.dmin = dmin; p.zq = zq; p.packed = packed; p.wdeq = wdeq; p.wdeq_dtype = GQ_F32;
-    p.flags = nullptr; p.clk = nullptr; p.nz2 = F2_NEG_ZERO2; p.static_scales = 0; p.perm = nullptr;
+    p.flags = nullptr; p.clk = nullptr; p.nz2 = F2_NEG_ZERO2; p.static_scales = static_scales; p.perm = perm;
     switch (qtype) {
     case GQ_Q2_K: run<GQ_Q2_K>(p, right_looking); return 0;
     case GQ_Q3_K: run<GQ_Q3_K>(p, right_looking); return 0;

@@ -238,3 +238,46 @@ def test_shipped_column_loop_kernel_matches_reference_golden(lib_layer, golden_d
         r = r.view(np.uint16) if r.dtype == np.float16 else r
         assert np.array_equal(a.view(np.uint8), r.view(np.uint8).reshape(a.shape[0], -1)), f"{k} differs from the reference"
     assert np.array_equal(wd, g[f"{tname}_ieee_dequant"]), "dequantised weights"
+
+
+@pytest.mark.parametrize("schedule", ["left_looking", "right_looking"])
+@pytest.mark.parametrize("variant", ["static", "actorder"])
+@pytest.mark.parametrize("tname", ["Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"])
+def test_shipped_column_loop_kernel_variants_match_reference_golden(lib_layer, golden_dir, tname, variant, schedule):
+    """static_groups and act_order (gptq.py:184-216, 233-238, 273-277) through the shipped kernels on the emulator, in the flow
+    of gq_gptq_quantize_ex / ops.gptq_quantize: scales searched up front by the RTN search over the un-permuted weights, the loop
+    on W[:, perm] with the factor of H[perm][:, perm], codes un-permuted afterwards -- against the reference's own outputs
+    (tests/golden/variants_a.npz).  Q3_K ignores both options like the reference (gptq.py:204-206)."""
+    g = np.load(os.path.join(golden_dir, "variants_a.npz"))
+    qt = {"Q2_K": 10, "Q3_K": 11, "Q4_K": 12, "Q5_K": 13, "Q6_K": 14}[tname]
+    gs = 32 if tname in ("Q4_K", "Q5_K") else 16
+    W0 = np.ascontiguousarray(g["W"], dtype=np.float32)
+    d_row, d_col = W0.shape
+    nsb = d_col // 256
+    uses_perm = variant == "actorder" and tname != "Q3_K"
+    static = tname != "Q3_K"
+    U = np.ascontiguousarray(g["U_perm"] if uses_perm else g["U_plain"], dtype=np.float32)
+    perm = np.ascontiguousarray(g["perm"].astype(np.int32)) if uses_perm else None
+    qw = np.zeros((d_row, d_col), np.uint8)
+    d = np.zeros((d_row, nsb), np.uint16)
+    dmin = np.zeros_like(d)
+    sq = np.zeros((d_row, d_col // gs), np.uint8)
+    zq = np.zeros_like(sq)
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    if static:
+        assert lib_layer.run_search_all(C.c_int(qt), p(W0, C.c_float), C.c_int(d_row), C.c_int(d_col), C.c_double(-1.0), C.c_double(0.1),
+                                        C.c_int(20), p(d, C.c_uint16), p(dmin, C.c_uint16), p(sq, C.c_uint8), p(zq, C.c_uint8)) == 0
+    W = np.ascontiguousarray(W0[:, perm] if uses_perm else W0).copy()
+    rc = lib_layer.run_gptq_layer_ex(C.c_int(qt), C.c_int(1 if schedule == "right_looking" else 0), p(W, C.c_float), p(U, C.c_float),
+                                     C.c_int(d_row), C.c_int(d_col), C.c_double(-1.0), C.c_double(0.1), C.c_int(20),
+                                     C.c_int((2 if uses_perm else 1) if static else 0), p(perm, C.c_int) if uses_perm else None,
+                                     p(qw, C.c_uint8), p(d, C.c_uint16), p(sq, C.c_uint8), p(dmin, C.c_uint16), p(zq, C.c_uint8), None, None)
+    assert rc == 0
+    if uses_perm:                      # gptq.py:276-277: qweight[:, invperm]
+        out = np.zeros_like(qw)
+        out[:, perm] = qw
+        qw = out
+    for k, a in (("qweight", qw), ("d", d), ("sq", sq), ("dmin", dmin), ("zq", zq)):
+        r = g[f"{variant}_{tname}_{k}"]
+        r = r.view(np.uint16) if r.dtype == np.float16 else r
+        assert np.array_equal(a.view(np.uint8), r.view(np.uint8).reshape(a.shape[0], -1)), f"{k} differs from the reference"
