@@ -281,3 +281,43 @@ def test_shipped_column_loop_kernel_variants_match_reference_golden(lib_layer, g
         r = g[f"{variant}_{tname}_{k}"]
         r = r.view(np.uint16) if r.dtype == np.float16 else r
         assert np.array_equal(a.view(np.uint8), r.view(np.uint8).reshape(a.shape[0], -1)), f"{k} differs from the reference"
+
+
+@pytest.mark.parametrize("schedule", ["left_looking", "right_looking"])
+def test_shipped_column_loop_kernel_unsafe_division_rerun(lib_layer, schedule):
+    """The rare path of the column steps: DivBy::div_fast flags quotients it cannot guarantee (a divisor whose significand is all
+    ones, dividends below 2^-60 or above 2^60), the warp then re-runs the 128-column block with IEEE divisions
+    (serial_block<>: __any_sync + serial_block_impl<QT, true>).  Crafted input: all-ones significands on the diagonal of U
+    (scales with all-ones significands come by themselves) and a row of tiny (1e-22) weights next to ordinary ones -- the
+    emulated shipped kernel must still equal the oracle bit for bit.  (Weights that overflow fp16 scales end in NaNs whose sign
+    bit is implementation noise; not part of this test.)"""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(11)
+    d_row, d_col = 40, 512
+    W = (rng.standard_normal((d_row, d_col)) * 0.05).astype(np.float32)
+    W[3] *= np.float32(1e-22)
+    W[17, 100:140] = 0.0
+    U = (np.triu(rng.standard_normal((d_col, d_col)) * 0.02)).astype(np.float32)
+    diag = (0.5 + rng.random(d_col)).astype(np.float32)
+    diag[::3] = np.frombuffer(np.array([0x3FFFFFFF, 0x3F7FFFFF, 0x407FFFFF], np.uint32).tobytes(), np.float32)[rng.integers(0, 3, len(diag[::3]))]
+    U[np.arange(d_col), np.arange(d_col)] = diag
+    for tname, qt, gs, ts in (("Q4_K", 12, 32, 144), ("Q6_K", 14, 16, 210)):
+        ref = orc.gptq_step(W.copy(), U, qt)
+        Wk = W.copy()
+        nsb = d_col // 256
+        qw = np.zeros((d_row, d_col), np.uint8)
+        d = np.zeros((d_row, nsb), np.uint16)
+        dmin = np.zeros_like(d)
+        sq = np.zeros((d_row, d_col // gs), np.uint8)
+        zq = np.zeros_like(sq)
+        pk = np.zeros((d_row, nsb * ts), np.uint8)
+        wd = np.zeros((d_row, d_col), np.float32)
+        p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        rc = lib_layer.run_gptq_layer(C.c_int(qt), C.c_int(1 if schedule == "right_looking" else 0), p(Wk, C.c_float), p(U, C.c_float),
+                                      C.c_int(d_row), C.c_int(d_col), C.c_double(-1.0), C.c_double(0.1), C.c_int(20), p(qw, C.c_uint8),
+                                      p(d, C.c_uint16), p(sq, C.c_uint8), p(dmin, C.c_uint16), p(zq, C.c_uint8), p(pk, C.c_uint8), p(wd, C.c_float))
+        assert rc == 0
+        for k, a, r in (("qweight", qw, ref[0]), ("d", d, ref[1]), ("sq", sq, ref[2]), ("dmin", dmin, ref[3]), ("zq", zq, ref[4])):
+            r = r.view(np.uint16) if r.dtype == np.float16 else r
+            assert np.array_equal(a.view(np.uint8), np.ascontiguousarray(r).view(np.uint8).reshape(a.shape[0], -1)), f"{tname}.{k}"
+        assert np.array_equal(pk, orc.pack(qt, *ref[:5]))
