@@ -13,32 +13,7 @@ namespace {
 constexpr int R = 32;
 constexpr int NT = 256;
 
-struct RtnParams {
-    const void *W;       // (d_row, *) of w_dtype, row stride ld_in elements
-    int w_dtype;
-    long ld_in;
-    int d_row, nsb;
-    SearchParams sp;
-    // metadata outputs: d/dmin at [row*d_stride + sb], sq/zq at [row*sq_stride + sb*GPR + g]
-    uint16_t *d, *dmin;
-    long d_stride;
-    uint8_t *sq, *zq;
-    long sq_stride;
-    // optional full-matrix outputs (row stride = nsb*256 elements)
-    uint8_t *qweight;
-    uint8_t *packed;
-    void *wdeq;
-    int wdeq_dtype;
-    uint32_t *flags;
-};
-
-struct __align__(16) RtnSmem {
-    float Wt[R * 256];
-    uint8_t codes[R * 256];
-    float gsc[R * 16];
-    float gzr[R * 16];
-    RowScales<R> rs;
-};
+#include "rtn_structs.cuh"      // RtnParams, RtnSmem (shared with the CPU suite's emulator harness)
 
 template <int QT>
 __global__ void __launch_bounds__(NT) rtn_kernel(const RtnParams p) {

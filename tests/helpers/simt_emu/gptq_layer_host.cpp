@@ -63,12 +63,7 @@ template <int QT> void run(LayerParams p, int right_looking) {
 
 // ---- static_groups (gptq.py:184-196): all scales up front = the RTN search over the whole matrix (gq_search_all_superblocks)
 namespace {
-struct RtnParams {
-    const void *W; int w_dtype; long ld_in; int d_row, nsb; SearchParams sp;
-    uint16_t *d, *dmin; long d_stride; uint8_t *sq, *zq; long sq_stride;
-    uint8_t *qweight; uint8_t *packed; void *wdeq; int wdeq_dtype; uint32_t *flags;
-};
-struct alignas(16) RtnSmem { float Wt[32 * 256]; uint8_t codes[32 * 256]; float gsc[32 * 16]; float gzr[32 * 16]; RowScales<32> rs; };
+#include "rtn_structs.cuh"          // rtn.cu's own RtnParams / RtnSmem (uses R == 32 of this namespace)
 RtnSmem g_rtn_sm;
 template <int QT> void search_all(const RtnParams &p) {
     simt::launch(dim3((p.d_row + 31) / 32, p.nsb), dim3(256), [&]() { rtn_body<QT, 32, 256, RtnParams, RtnSmem>(p, g_rtn_sm); });

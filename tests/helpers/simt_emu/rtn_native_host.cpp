@@ -1,5 +1,5 @@
 // TEST-ONLY: gptq_gguf_toolkit_b200/csrc/rtn_native.cuh (the experimental native-arithmetic RTN kernel, not yet run on a GPU) on
-// the SIMT emulator, with the CUDA intrinsics from tests/helpers/host_shim.  RtnParams / RtnSmem below restate rtn.cu's.
+// the SIMT emulator, with the CUDA intrinsics from tests/helpers/host_shim.  RtnParams / RtnSmem are rtn.cu's own (rtn_structs.cuh).
 #define SIMT_EMU 1
 #define GQ_HOST_SHIM 1
 #include "simt_emu.h"
@@ -8,12 +8,7 @@
 
 namespace {
 constexpr int R = 32, NT = 256;
-struct RtnParams {
-    const void *W; int w_dtype; long ld_in; int d_row, nsb; SearchParams sp;
-    uint16_t *d, *dmin; long d_stride; uint8_t *sq, *zq; long sq_stride;
-    uint8_t *qweight; uint8_t *packed; void *wdeq; int wdeq_dtype; uint32_t *flags;
-};
-struct alignas(16) RtnSmem { float Wt[R * 256]; uint8_t codes[R * 256]; float gsc[R * 16]; float gzr[R * 16]; RowScales<R> rs; };
+#include "rtn_structs.cuh"          // rtn.cu's own RtnParams / RtnSmem
 RtnSmem g_sm;       // one block at a time: the block's shared memory
 
 template <int QT, int RND> void run(const RtnParams &p) {
