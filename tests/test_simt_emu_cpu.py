@@ -321,3 +321,31 @@ def test_shipped_column_loop_kernel_unsafe_division_rerun(lib_layer, schedule):
             r = r.view(np.uint16) if r.dtype == np.float16 else r
             assert np.array_equal(a.view(np.uint8), np.ascontiguousarray(r).view(np.uint8).reshape(a.shape[0], -1)), f"{tname}.{k}"
         assert np.array_equal(pk, orc.pack(qt, *ref[:5]))
+
+
+def test_shipped_simt_hessian_kernel_on_the_emulator(tmp_path_factory):
+    """sg::sgemm_kernel (csrc/sgemm.cuh) in the configuration gq_hessian_update uses for fp32 activations: H <- beta H + alpha
+    X^T X over upper tiles with the mirrored store -- against float64, exact symmetry, two accumulation steps (GPTQ.update's
+    running average, gptq.py:108-112), a token count that is not a multiple of the k tile."""
+    so = str(tmp_path_factory.mktemp("emu") / "libsgemm_emu.so")
+    cmd = ["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-I", EMU,
+           "-I", os.path.join(ROOT, "tests", "helpers", "host_shim"), "-I", os.path.join(ROOT, "gptq_gguf_toolkit_b200", "csrc"),
+           os.path.join(EMU, "sgemm_host.cpp"), "-o", so]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-4000:]
+    lib = C.CDLL(so)
+    lib.run_hessian_simt.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_long, C.c_int, C.c_float, C.c_float]
+    rng = np.random.default_rng(5)
+    d_col = 256
+    H = np.zeros((d_col, d_col), np.float32)
+    want = np.zeros((d_col, d_col), np.float64)
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    n = 0
+    for n_tok in (200, 77):
+        X = (rng.standard_normal((n_tok, d_col)) * np.exp(0.3 * rng.standard_normal(d_col))).astype(np.float32)
+        beta, alpha = n / (n + 1), 2.0 / (n + 1)
+        lib.run_hessian_simt(p(H), p(X), n_tok, d_col, beta, alpha)
+        want = beta * want + alpha * (X.astype(np.float64).T @ X.astype(np.float64))
+        n += 1
+    assert np.array_equal(H, H.T), "H must be exactly symmetric"
+    assert np.abs(H - want).max() <= 5e-5 * np.abs(want).max()
