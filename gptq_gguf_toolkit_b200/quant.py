@@ -69,6 +69,9 @@ def parse_args(argv=None):
     p.add_argument("--random_init_config", type=str, default=None,
                    help="JSON file with LlamaConfig kwargs: build a random-init model instead of loading weights")
     p.add_argument("--no_share_hessians", action="store_true")
+    p.add_argument("--rtn_fp32_arith", action="store_true",
+                   help="embed_tokens / lm_head of a 16-bit model: widen the weights to fp32 for the scale search instead of "
+                        "searching in the weight's own arithmetic like the reference does")
     return p.parse_args(argv)
 
 
@@ -150,7 +153,8 @@ def main(argv=None):
         post_block_modules=args.post_block_modules, quant_non_block_modules=args.quant_non_block_modules,
         cpu_offload_modules=args.cpu_offload_modules, cpu_offload_activations=args.cpu_offload_activations,
         device=device, verbose=args.verbose, save_dir=args.save_dir,
-        calibration_batch_size=args.calibration_batch_size, share_hessians=not args.no_share_hessians, timer=timer)
+        calibration_batch_size=args.calibration_batch_size, share_hessians=not args.no_share_hessians, timer=timer,
+        rtn_native_arith=not args.rtn_fp32_arith)
     if rank == 0:
         os.makedirs(args.save_dir, exist_ok=True)
     if distributed:

@@ -120,7 +120,7 @@ class Quantizer:
                  calibration_batch_size: int = 8, share_hessians: bool = True, keep_results: bool = False,
                  save_packed: bool = True, timer: Optional[PhaseTimer] = None, early_exit_pass1: bool = True,
                  overlap_prepare: bool = True, defer_last_layer: bool = True, fused_forward_ops: bool = True,
-                 early_prepare: bool = True, rtn_native_arith: bool = False) -> None:
+                 early_prepare: bool = True, rtn_native_arith: bool = True) -> None:
         self.model = model
         self.data_loader = data_loader
         self.quantizable_modules = quantizable_modules
@@ -143,8 +143,8 @@ class Quantizer:
         self.defer_last_layer = defer_last_layer
         self.fused_forward_ops = fused_forward_ops
         self.early_prepare = early_prepare
-        # EXPERIMENTAL: embed_tokens / lm_head of a bf16 model with the scale search in bf16 arithmetic like the reference
-        # (gq_rtn_quantize_native); default off = weights widened to fp32
+        # embed_tokens / lm_head of a 16-bit model: scale search in the weight's own arithmetic like the reference
+        # (quantizer.py:303-305 -> gq_rtn_quantize_native); False = weights widened to fp32
         self.rtn_native_arith = rtn_native_arith
         self.fused_installed: List[str] = []
         self._split_ok: Optional[bool] = None
