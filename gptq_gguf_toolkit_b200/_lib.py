@@ -42,6 +42,7 @@ SIGNATURES = {
     "gq_gptq_quantize_ex": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _d, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "gq_profile_enable": (None, [_i]),
     "gq_profile_read": (_i, [C.POINTER(_f), C.POINTER(_i)]),
+    "gq_profile_read3": (_i, [C.POINTER(_f), C.POINTER(_i)]),
     "gq_rtn_quantize": (_i, [_vp, _i, _i, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "gq_rtn_quantize_native": (_i, [_vp, _i, _i, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "gq_get_scale_and_zero": (_i, [_vp, _l, _i, _i, _d, _d, _i, _vp, _vp, _l, _vp, _vp, _l, _vp, _vp]),

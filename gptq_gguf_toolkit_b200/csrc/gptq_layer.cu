@@ -14,7 +14,7 @@
 //   * The scale/min search, the 128 sequential column steps (rank-1 updates held in registers, 8 lanes
 //     per row), the GGUF bit-pack and the dequantised write-back are fused in shared memory.
 #include "f32x2.cuh"
-#include "gemm_tf32.cuh"
+#include "gemm_f16x3.cuh"
 #include "tile.cuh"
 #include "rank_update.cuh"
 #include "exact_update_v2.cuh"
@@ -95,7 +95,7 @@ void gq_fill_search_params(SearchParams &sp, int maxq, double rmin, double rdelt
 // ---- optional kernel-level profiling of the fast path (bench.py: rank-k GEMM time measured live with CUDA events) ----
 #include <vector>
 namespace {
-struct ProfEvent { cudaEvent_t a, b; int kind; };   // kind 0 = fused search/column-loop kernel, 1 = rank-k update launch (tcgen05 GEMM / exact_update_kernel)
+struct ProfEvent { cudaEvent_t a, b; int kind; };   // kind 0 = fused search/column-loop kernel, 1 = rank-k update launch (tcgen05 GEMM / exact_update_kernel), 2 = operand preparation of the tcgen05 GEMM
 bool g_prof_on = false;
 std::vector<ProfEvent> g_prof;
 struct ProfScope {
@@ -115,8 +115,8 @@ unsigned long long *g_phase_clk = nullptr;
 extern "C" GQ_API void gq_debug_phase_clocks(unsigned long long *dev8) { g_phase_clk = dev8; }
 extern "C" GQ_API void gq_profile_enable(int on) { g_prof_on = on != 0; }
 // Synchronises, sums the recorded spans by kind (milliseconds, launch counts), clears the record.
-extern "C" GQ_API int gq_profile_read(float ms[2], int counts[2]) {
-    ms[0] = ms[1] = 0.f; counts[0] = counts[1] = 0;
+extern "C" GQ_API int gq_profile_read3(float ms[3], int counts[3]) {
+    for (int k = 0; k < 3; ++k) { ms[k] = 0.f; counts[k] = 0; }
     for (auto &e : g_prof) {
         if (cudaEventSynchronize(e.b) != cudaSuccess) return GQ_ERR_CUDA;
         float t = 0.f;
@@ -127,27 +127,42 @@ extern "C" GQ_API int gq_profile_read(float ms[2], int counts[2]) {
     g_prof.clear();
     return GQ_OK;
 }
+extern "C" GQ_API int gq_profile_read(float ms[2], int counts[2]) {      // kinds 0 and 1 only (kind 2 is dropped)
+    float m3[3]; int c3[3];
+    const int rc = gq_profile_read3(m3, c3);
+    ms[0] = m3[0]; ms[1] = m3[1]; counts[0] = c3[0]; counts[1] = c3[1];
+    return rc;
+}
 
 namespace {
 
-// Ut = U^T split into TF32 hi / lo parts (fast mode's B operand must be K-contiguous: B[n][k] = U[k][n] = Ut[n][k])
-__global__ void __launch_bounds__(256) transpose_split_kernel(const float *__restrict__ U, int n, float *__restrict__ hi,
-                                                              float *__restrict__ lo) {
-    __shared__ float t[32][33];
-    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int r = ty; r < 32; r += 8) t[r][tx] = U[(size_t)(r0 + r) * n + c0 + tx];
-    __syncthreads();
-    for (int c = ty; c < 32; c += 8) {
-        const float x = t[tx][c];
-        const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-        hi[(size_t)(c0 + c) * n + r0 + tx] = h;
-        lo[(size_t)(c0 + c) * n + r0 + tx] = __fsub_rn(x, h);
-    }
-}
-
+// ---- GQ_MODE_FAST workspace: U^T as a split-fp16 operand (n rows of 2n halves) | its column scales | column-max scratch |
+// the split errors of one update (rows padded to 128, up to FAST_KMAX k's) | their row scales
+constexpr int FAST_KMAX = 1024;
+struct FastWs { __half *ut; float *sb; unsigned int *cmax; __half *e16; float *sa; };
+inline size_t al1k(size_t x) { return (x + 1023) / 1024 * 1024; }
 size_t fast_ws_bytes(int d_row, int d_col) {
     const size_t n = (size_t)d_col, mp = ((size_t)d_row + 127) / 128 * 128;
-    return 2 * n * n * sizeof(float) + 2 * mp * 256 * sizeof(float) + 4096;
+    return 1024 + al1k(4 * n * n) + 2 * al1k(4 * n) + al1k(mp * 2 * FAST_KMAX * 2) + al1k(4 * mp);
+}
+FastWs fast_ws_carve(void *ws, int d_row, int d_col) {
+    const size_t n = (size_t)d_col, mp = ((size_t)d_row + 127) / 128 * 128;
+    uint8_t *b = reinterpret_cast<uint8_t *>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+    FastWs w;
+    w.ut = (__half *)b; b += al1k(4 * n * n);
+    w.sb = (float *)b; b += al1k(4 * n);
+    w.cmax = (unsigned int *)b; b += al1k(4 * n);
+    w.e16 = (__half *)b; b += al1k(mp * 2 * FAST_KMAX * 2);
+    w.sa = (float *)b;
+    return w;
+}
+// Super-blocks per trailing update (GQ_FAST_GROUP = 1, 2 or 4; read once per layer): inside a group of G super-blocks the updates stay
+// inside the group (K = 256), the columns behind the group receive ONE update with K = 256 G -- G times fewer passes over
+// the trailing part of W (the K = 256 update moves 64 flop per byte of W, HBM-bound well below the tensor pipe).
+int fast_group() {
+    const char *e = getenv("GQ_FAST_GROUP");
+    const int v = e ? atoi(e) : 2;
+    return (v == 1 || v == 2 || v == 4) ? v : 2;
 }
 
 template <int QT> int run_layer(LayerParams p, int mode, void *ws, size_t ws_bytes, cudaStream_t st) {
@@ -186,37 +201,51 @@ template <int QT> int run_layer(LayerParams p, int mode, void *ws, size_t ws_byt
         }
         return GQ_OK;
     }
-    // ---- GQ_MODE_FAST: right-looking at super-block granularity.  Per 256-column super-block one launch of the fused
-    // search / column-loop kernel, then ONE tcgen05 3xTF32 GEMM  W[:, c+256:] -= E[:, c:c+256] * U[c:c+256, c+256:].
+    // ---- GQ_MODE_FAST: right-looking with the rank-k updates on tcgen05 (split-fp16 GEMM, gemm_f16x3.cu).  Per 256-column
+    // super-block one launch of the fused search / column-loop kernel; its errors E (left in W[:, c:c+256]) then update
+    //   * the rest of its group of G super-blocks:      W[:, c+256:gend]  -= E_c     U[c:c+256,  c+256:gend]    (K = 256)
+    //   * after the group's last super-block, all later columns:  W[:, gend:] -= E_group U[g0:gend, gend:]      (K = 256 G)
     if (ws == nullptr || ws_bytes < fast_ws_bytes(p.d_row, p.d_col)) {
         gq_set_error("gq_gptq_quantize: fast mode needs %zu workspace bytes", fast_ws_bytes(p.d_row, p.d_col));
         return GQ_ERR_WORKSPACE;
     }
-    const int n = p.d_col, mp = (p.d_row + 127) / 128 * 128;
-    float *ut_hi = reinterpret_cast<float *>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
-    float *ut_lo = ut_hi + (size_t)n * n;
-    float *e_hi = ut_lo + (size_t)n * n;
-    float *e_lo = e_hi + (size_t)mp * 256;
-    GQ_CHECK_CUDA(cudaMemsetAsync(e_hi, 0, 2 * (size_t)mp * 256 * sizeof(float), st));   // padded rows stay zero
-    transpose_split_kernel<<<dim3(n / 32, n / 32), 256, 0, st>>>(p.U, n, ut_hi, ut_lo);
-    gq_count_launches(1);
-    p.fast = 1; p.skip_bulk = 1; p.e_hi = e_hi; p.e_lo = e_lo;
-    for (int sb = 0; sb < nsb; ++sb) {
-        p.sb_begin = sb; p.sb_end = sb + 1;
-        int rc;
-        {
-            ProfScope ps(st, 0);
-            rc = launch_layer<QT>(p, st);
-        }
+    const int n = p.d_col, mp = (p.d_row + 127) / 128 * 128, G = fast_group();
+    const FastWs w = fast_ws_carve(ws, p.d_row, p.d_col);
+    {
+        ProfScope ps(st, 2);
+        const int rc = th::transpose_split_upper_f16(p.U, n, w.ut, w.sb, w.cmax, st);
         if (rc) return rc;
-        const int c = sb * GQ_QK_K, ntrail = n - c - GQ_QK_K;
-        if (ntrail > 0) {
-            tg::PreSplit A{e_hi, e_lo, 256, mp, 0, 0};
-            tg::PreSplit B{ut_hi, ut_lo, n, n, c + GQ_QK_K, c};
+    }
+    auto update = [&](int k0, int K, int n0, int N) -> int {
+        {
+            ProfScope ps(st, 2);
+            const int rc = th::split_rows_f16(p.W + k0, p.d_col, 0, p.d_row, mp, K, K, 1, w.e16, w.sa, st);
+            if (rc) return rc;
+        }
+        const th::Split16 A{w.e16, w.sa, 2L * K, mp, 0, 0};
+        const th::Split16 B{w.ut, w.sb, 2L * n, n, n0, k0};
+        ProfScope ps(st, 1);
+        return th::gemm_f16x3_nt_presplit(A, B, p.W + n0, p.d_col, mp, p.d_row, N, K, -1.0f, 1.0f, st);
+    };
+    p.skip_bulk = 1;
+    for (int g0 = 0; g0 < nsb; g0 += G) {
+        const int g1 = g0 + G < nsb ? g0 + G : nsb, gend = g1 * GQ_QK_K;
+        for (int sb = g0; sb < g1; ++sb) {
+            p.sb_begin = sb; p.sb_end = sb + 1;
+            int rc;
             {
-                ProfScope ps(st, 1);
-                rc = tg::gemm_tf32x3_nt_presplit(A, B, p.W + c + GQ_QK_K, p.d_col, mp, p.d_row, ntrail, GQ_QK_K, -1.0f, 1.0f, st);
+                ProfScope ps(st, 0);
+                rc = launch_layer<QT>(p, st);
             }
+            if (rc) return rc;
+            const int c = sb * GQ_QK_K;
+            if (gend - c - GQ_QK_K > 0) {
+                rc = update(c, GQ_QK_K, c + GQ_QK_K, gend - c - GQ_QK_K);
+                if (rc) return rc;
+            }
+        }
+        if (n - gend > 0) {
+            const int rc = update(g0 * GQ_QK_K, gend - g0 * GQ_QK_K, gend, n - gend);
             if (rc) return rc;
         }
     }

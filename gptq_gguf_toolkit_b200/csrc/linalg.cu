@@ -15,12 +15,16 @@
 #include <vector>
 
 #include "chol_diag_v3.cuh"
+#include "gemm_f16x3.cuh"
 #include "gemm_tf32.cuh"
 #include "sgemm.cuh"
 
 namespace {
 
 constexpr int NB = 128;   // panel width
+#ifndef GQ_PREPARE_F16_DEFAULT
+#define GQ_PREPARE_F16_DEFAULT false
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // masks and damping
@@ -272,6 +276,12 @@ int prepare_diag_variant() {      // GQ_DIAG_V2: 0 = chol_diag_kernel, 1 (defaul
     const char *e = getenv("GQ_DIAG_V2");      // read on every call: tests and micro-benchmarks flip it at run time
     return (e && e[0] == '0') ? 0 : (e && e[0] == '3') ? 3 : 1;
 }
+// GQ_PREPARE_GEMM=tf32|f16 (read on every call: tests and micro-benchmarks flip it): which tcgen05 GEMM the chain uses --
+// 3xTF32 (gemm_tf32.cu) or split-fp16 (gemm_f16x3.cu: half the operand bytes, twice the MMA rate, same 22-bit operands).
+bool prepare_use_f16() {
+    const char *e = getenv("GQ_PREPARE_GEMM");
+    return e ? (e[0] == 'f') : GQ_PREPARE_F16_DEFAULT;
+}
 bool prepare_use_simt() {
     static int v = -1;
     if (v < 0) { const char *e = getenv("GQ_PREPARE_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -297,7 +307,7 @@ extern "C" int gq_prepare(float *H, const float *W, int d_row, int d_col, float 
     cudaStream_t st = (cudaStream_t)stream;
     const int n = d_col;
     const long ld = n;
-    const bool simt = prepare_use_simt();
+    const bool simt = prepare_use_simt(), use_f16 = prepare_use_f16();
     float *A = (float *)workspace;
     float *Li = A + (size_t)n * n;
     float *LiT = Li + (size_t)n * n;
@@ -333,7 +343,7 @@ extern "C" int gq_prepare(float *H, const float *W, int d_row, int d_col, float 
         g.A = Ap; g.lda = ld; g.a_batch = ab; g.B = Bp; g.ldb = ld; g.b_batch = bb; g.C = Cp; g.ldc = ld; g.c_batch = cb;
         g.M = M; g.N = N; g.K = K; g.batch = batch; g.alpha = alpha; g.beta = beta; g.tile_mode = tile_mode; g.k_mode = k_mode;
         g.same_ab = same;
-        return tg::gemm_tf32x3_nt(g, ws_, sws_bytes, stream_);
+        return use_f16 ? th::gemm_f16x3_nt(g, ws_, sws_bytes, stream_) : tg::gemm_tf32x3_nt(g, ws_, sws_bytes, stream_);
     };
     auto tc_gemm = [&](const float *Ap, const float *Bp, float *Cp, int M, int N, int K, int batch, long ab, long bb, long cb,
                        float alpha, float beta, int tile_mode, int k_mode, bool same) {

@@ -47,12 +47,15 @@ def profile_enable(on: bool) -> None:
 
 
 def profile_read() -> dict:
-    """{'panel_ms', 'panel_launches', 'rankk_gemm_ms', 'rankk_gemm_launches'} since the last read; synchronises."""
+    """{'panel_ms', 'panel_launches', 'rankk_gemm_ms', 'rankk_gemm_launches', 'split_ms', 'split_launches'} since the last
+    read; synchronises.  rankk_* = the rank-k update launches (tcgen05 GEMM in fast mode, exact_update_kernel otherwise),
+    split_* = the operand preparation of fast mode's GEMMs (fp16 hi/lo split of the errors, once per layer of U^T)."""
     import ctypes as C
-    ms = (C.c_float * 2)()
-    n = (C.c_int * 2)()
-    L.check(L.load().gq_profile_read(ms, n))
-    return {"panel_ms": ms[0], "panel_launches": n[0], "rankk_gemm_ms": ms[1], "rankk_gemm_launches": n[1]}
+    ms = (C.c_float * 3)()
+    n = (C.c_int * 3)()
+    L.check(L.load().gq_profile_read3(ms, n))
+    return {"panel_ms": ms[0], "panel_launches": n[0], "rankk_gemm_ms": ms[1], "rankk_gemm_launches": n[1],
+            "split_ms": ms[2], "split_launches": n[2]}
 
 
 def _workspace(device, nbytes: int, slot: int = 0) -> torch.Tensor:

@@ -53,7 +53,7 @@ typedef enum { GQ_Q2_K = 10, GQ_Q3_K = 11, GQ_Q4_K = 12, GQ_Q5_K = 13, GQ_Q6_K =
 typedef enum { GQ_F32 = 0, GQ_F16 = 1, GQ_BF16 = 2 } gq_dtype;
 
 /* GQ_MODE_EXACT reproduces the reference's CPU arithmetic bit for bit given the same (W, U).
- * GQ_MODE_FAST runs the rank-k update on tcgen05 tensor cores (3xTF32); not bit-identical.
+ * GQ_MODE_FAST runs the rank-k update on tcgen05 tensor cores (split-fp16 operands, fp32 accumulation); not bit-identical.
  * The exact arithmetic has two bit-identical schedules: ONE left-looking launch per layer (every 32-row CTA applies all
  * earlier blocks to its own tile), and a right-looking one (per 256-column super-block a panel launch + an exact FFMA
  * update of the whole trailing part by all SMs) that wins when a launch has few rows and many columns (a row slice of
@@ -115,7 +115,7 @@ GQ_API int gq_prepare(float *H, const float *W, int d_row, int d_col, float rel_
  *          two can differ.  Must be zero-initialised by the caller.
  * block_size must be 128 (the reference's run_quant.sh default).
  * mode GQ_MODE_FAST needs gq_gptq_workspace_bytes() of scratch (the exact modes need none): the rank-k updates between
- * 256-column super-blocks then run as tcgen05 3xTF32 GEMMs (fp32-class accuracy, NOT bit-identical to the reference).
+ * 256-column super-blocks then run as tcgen05 split-fp16 GEMMs (fp32-class accuracy, NOT bit-identical to the reference).
  * GQ_MODE_EXACT / _LEFT / _RIGHT give bit-identical outputs (see gq_mode); they differ in the number of launches. */
 GQ_API size_t gq_gptq_workspace_bytes(int d_row, int d_col, int mode);
 GQ_API int gq_gptq_quantize(float *W, const float *U, int d_row, int d_col, int qtype, int block_size,
@@ -145,6 +145,8 @@ GQ_API int gq_gptq_quantize_ex(float *W, const float *U, int d_row, int d_col, i
  * gq_profile_read synchronises on the recorded events, returns summed milliseconds and launch counts per kind, and clears. */
 GQ_API void gq_profile_enable(int on);
 GQ_API int gq_profile_read(float ms[2], int counts[2]);
+/* Same with kind 2 = the operand preparation (fp16 hi/lo split) launches of GQ_MODE_FAST's GEMMs as a third entry. */
+GQ_API int gq_profile_read3(float ms[3], int counts[3]);
 
 /* RTN K-quant without a Hessian -- replaces Quantizer._quant_non_block_module
  * (quantizer.py:278-330).  W: (d_row, d_col) of w_dtype, read-only; arithmetic is fp32. */

@@ -68,6 +68,14 @@ def main():
                 mn, av = timed(lambda: ops.prepare(H0.clone(), W, 0.01), warm=1, it=2)
                 print(f"prepare n={n} GQ_DIAG_V2={v}: {mn:.2f} ms (avg {av:.2f}), launches/call {(ops.launch_count() - l0) // 3}", flush=True)
             os.environ["GQ_DIAG_V2"] = "1"
+            for be in ("tf32", "f16"):      # tcgen05 GEMM back-end of the chain
+                os.environ["GQ_PREPARE_GEMM"] = be
+                for v in ("1", "3"):
+                    os.environ["GQ_DIAG_V2"] = v
+                    mn, av = timed(lambda: ops.prepare(H0.clone(), W, 0.01), warm=1, it=2)
+                    print(f"prepare n={n} GQ_PREPARE_GEMM={be} GQ_DIAG_V2={v}: {mn:.2f} ms (avg {av:.2f})", flush=True)
+            os.environ.pop("GQ_PREPARE_GEMM", None)
+            os.environ["GQ_DIAG_V2"] = "1"
             if "experimental" in what and n >= 8192:      # look-ahead Cholesky (GQ_PREPARE_LOOKAHEAD=1), checked against the default U
                 Hc = H0.clone(); U_ref, _ = ops.prepare(Hc, W, 0.01)
                 os.environ["GQ_PREPARE_LOOKAHEAD"] = "1"
@@ -94,13 +102,17 @@ def main():
             fl = rows * n * (n - 128)
             print(f"gptq {rows}x{n}: {mn:.2f} ms -> rank-k {fl / mn / 1e9:.1f} TFLOP/s", flush=True)
             phase_clocks(lambda: ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16), (rows + 31) // 32)
-            mn, av = timed(lambda: ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16, mode=1), warm=1, it=2)
-            ops.profile_enable(True)
-            ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16, mode=1)
-            pr = ops.profile_read()
-            ops.profile_enable(False)
-            print(f"gptq FAST {rows}x{n}: {mn:.2f} ms -> rank-k {fl / mn / 1e9:.1f} TFLOP/s; panel {pr['panel_ms']:.2f} ms/{pr['panel_launches']}, "
-                  f"tcgen05 rank-k GEMMs {pr['rankk_gemm_ms']:.2f} ms/{pr['rankk_gemm_launches']} -> {rows * n * (n - 256) / max(pr['rankk_gemm_ms'], 1e-9) / 1e9:.0f} TFLOP/s", flush=True)
+            for grp in ("1", "2", "4"):
+                os.environ["GQ_FAST_GROUP"] = grp
+                mn, av = timed(lambda: ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16, mode=1), warm=1, it=2)
+                ops.profile_enable(True)
+                ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16, mode=1)
+                pr = ops.profile_read()
+                ops.profile_enable(False)
+                print(f"gptq FAST group={grp} {rows}x{n}: {mn:.2f} ms -> rank-k {fl / mn / 1e9:.1f} TFLOP/s; panel {pr['panel_ms']:.2f} ms/{pr['panel_launches']}, "
+                      f"split {pr['split_ms']:.2f} ms/{pr['split_launches']}, "
+                      f"tcgen05 rank-k GEMMs {pr['rankk_gemm_ms']:.2f} ms/{pr['rankk_gemm_launches']} -> {rows * n * (n - 256) / max(pr['rankk_gemm_ms'], 1e-9) / 1e9:.0f} TFLOP/s", flush=True)
+            os.environ.pop("GQ_FAST_GROUP", None)
     if "schedules" in what:
         # the two bit-identical schedules of the exact arithmetic on row slices (what one rank of an N-GPU run launches)
         for rows, n in ((4096, 14336), (2048, 14336), (1024, 14336), (512, 14336), (4096, 4096), (512, 4096), (28672, 4096), (14336, 4096), (3584, 4096), (6144, 4096), (3072, 4096), (768, 4096)):

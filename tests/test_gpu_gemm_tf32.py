@@ -1,5 +1,6 @@
-"""GPU: the 3xTF32 tcgen05 GEMM building block (csrc/gemm_tf32.cu) against fp64 matmul.
-Tolerance: fp32-class -- max error <= 2e-6 of the largest |sum_k |a||b|| term (plain TF32 would be ~5e-4)."""
+"""GPU: the two fp32-class tcgen05 GEMM building blocks -- 3xTF32 (csrc/gemm_tf32.cu) and split-fp16 (csrc/gemm_f16x3.cu: the
+rank-k update of GQ_MODE_FAST) -- against fp64 matmul.
+Tolerance: fp32-class -- max error <= 2e-6 of the largest |sum_k |a||b|| term (plain TF32 / fp16 would be ~5e-4)."""
 import ctypes as C
 
 import pytest
@@ -8,17 +9,17 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def gemm():
+@pytest.fixture(scope="module", params=["tf32x3", "f16x3"])
+def gemm(request):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from gptq_gguf_toolkit_b200 import _lib
     lib = _lib.load()
-    f = lib.gq_debug_gemm_tf32x3_nt
+    f = getattr(lib, f"gq_debug_gemm_{request.param}_nt")
     f.restype = C.c_int
     f.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int,
                   C.c_long, C.c_long, C.c_long, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
-    w = lib.gq_debug_gemm_tf32x3_workspace
+    w = getattr(lib, f"gq_debug_gemm_{request.param}_workspace")
     w.restype = C.c_size_t
     w.argtypes = [C.c_int] * 4
 
@@ -39,7 +40,7 @@ def _check(got, ref, scale):
     assert err <= 2e-6 * scale, (err, scale)
 
 
-@pytest.mark.parametrize("shape", [(128, 128, 128), (256, 384, 96), (1024, 512, 2048), (2048, 2048, 1000)])
+@pytest.mark.parametrize("shape", [(128, 128, 128), (256, 384, 96), (1024, 512, 2048), (2048, 2048, 1000), (384, 1280, 512)])
 def test_gemm_full(gemm, shape):
     M, N, K = shape
     torch.manual_seed(M + N + K)
@@ -85,3 +86,18 @@ def test_gemm_triangular_k_ranges_and_batch(gemm):
     Cb = torch.zeros(3, 128, 256, device="cuda")
     gemm(A, B, Cb, batch=3, strides=(128 * 128, 256 * 128, 128 * 256))
     _check(Cb, A.double() @ B.double().transpose(1, 2), 128 * 16.0)
+
+
+def test_gemm_wide_dynamic_range_inside_rows(gemm):
+    """Elements of one operand row spanning 2^+-12 (the fp16 pair keeps fewer bits of the small ones): the error stays fp32-class
+    relative to the row's |a||b| sum, which is what a dot product's fp32 rounding is relative to as well."""
+    torch.manual_seed(5)
+    M, N, K = 256, 512, 768
+    A = torch.randn(M, K, device="cuda") * torch.exp2(torch.randint(-12, 13, (M, K), device="cuda").float()) * 1e-3
+    B = torch.randn(N, K, device="cuda") * torch.exp2(torch.randint(-12, 13, (N, K), device="cuda").float()) * 1e3
+    Cm = torch.zeros(M, N, device="cuda")
+    gemm(A, B, Cm)
+    # 5e-6: the tensor core's truncating fp32 accumulation shows on sums dominated by a few huge terms (measured on B200:
+    # 4.0e-6 for 3xTF32, below 2e-6 for the fp16 pair)
+    err = (Cm.double() - A.double() @ B.double().T).abs().max().item()
+    assert err <= 5e-6 * (A.double().abs() @ B.double().abs().T).max().item()
