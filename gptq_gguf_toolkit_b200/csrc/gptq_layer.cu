@@ -17,7 +17,6 @@
 #include "gemm_f16x3.cuh"
 #include "tile.cuh"
 #include "rank_update.cuh"
-#include "exact_update_v2.cuh"
 #include <cmath>
 #include <cstdlib>
 
@@ -61,16 +60,6 @@ int launch_exact_update(const LayerParams &p, int c, cudaStream_t st) {
     const int nwin = (p.d_col - c - GQ_QK_K) / GQ_QK_K;
     if (nwin <= 0) return GQ_OK;
     dim3 grid(nwin, (p.d_row + R - 1) / R);
-    const char *v2 = getenv("GQ_UPDATE_V2");      // experimental variant, see exact_update_v2_kernel
-    if (v2 && v2[0] == '1') {
-        static_assert(upd2::R == R && upd2::KP == KP && upd2::S == S, "exact_update_v2.cuh must use the pipeline geometry of this file");
-        const upd2::Params p2{p.W, p.U, p.d_row, p.d_col};
-        GQ_CHECK_CUDA(cudaFuncSetAttribute(exact_update_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd2::SMEM_BYTES));
-        exact_update_v2_kernel<<<grid, upd2::NT2, upd2::SMEM_BYTES, st>>>(p2, c);
-        gq_count_launches(1);
-        GQ_CHECK_CUDA(cudaGetLastError());
-        return GQ_OK;
-    }
     exact_update_kernel<<<grid, NT, smem, st>>>(p, c);
     gq_count_launches(1);
     GQ_CHECK_CUDA(cudaGetLastError());

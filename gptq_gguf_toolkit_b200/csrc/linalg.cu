@@ -10,11 +10,10 @@
 // The triangular inverse is a log-depth pairwise merge  inv([[A,0],[C,B]]) = [[Ai,0],[-Bi C Ai, Bi]],
 // whose work is all GEMM (zero tiles of the triangular factors are skipped).
 #include <cstdlib>
-#include <map>
-#include <mutex>
 #include <vector>
 
 #include "chol_diag_v3.cuh"
+#include "chol_diag_v4.cuh"
 #include "gemm_f16x3.cuh"
 #include "gemm_tf32.cuh"
 #include "sgemm.cuh"
@@ -23,7 +22,7 @@ namespace {
 
 constexpr int NB = 128;   // panel width
 #ifndef GQ_PREPARE_F16_DEFAULT
-#define GQ_PREPARE_F16_DEFAULT false
+#define GQ_PREPARE_F16_DEFAULT true
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -245,36 +244,19 @@ extern "C" int gq_pre_step(float *H, float *W, int d_row, int d_col, gq_stream_t
 // workspace: A (n*n) | Linv (n*n) | Linv^T (n*n) | nz (n ints) + flag | 3xTF32 operand splits
 namespace {
 size_t split_ws_bytes(size_t n) { return (size_t)(1.25 * (double)n * (double)n) * sizeof(float) + (n * 512 + 1024) * sizeof(float) + 8192; }
-// EXPERIMENTAL (GQ_PREPARE_LOOKAHEAD=1; off by default, not yet run on hardware -- written at the end of round 1 after the
-// GPU budget was spent).  Look-ahead for the blocked Cholesky at n >= 8192: after the panel solve only the NEXT block column
-// is updated on the chain's stream; the rest of the trailing update goes to an auxiliary stream with its own operand-split
-// workspace and is waited for one step later, so that a step costs diag + panel + one block column instead of
-// diag + panel + the whole trailing update.
-bool prepare_lookahead() {
-    const char *e = getenv("GQ_PREPARE_LOOKAHEAD");
-    return e && e[0] == '1';
+// Steps per trailing update of the blocked Cholesky (GQ_PREPARE_GROUP = 1, 2, 4 or 8; read on every call).  With G > 1 the
+// factorisation is left-looking inside a group of G block columns (a block column receives the group's earlier columns in ONE
+// skinny GEMM right before it is factored) and right-looking between groups (ONE rank-128 G update of everything behind the
+// group): the trailing matrix -- 411 MB on average at n = 14336, far beyond L2 -- is read and written n/(128 G) times instead
+// of n/128 times, which is what bounded the rank-128 updates (32 flop per byte of C).
+int prepare_group() {
+    const char *e = getenv("GQ_PREPARE_GROUP");
+    const int v = e ? atoi(e) : 4;
+    return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4;
 }
-struct LookaheadCtx { cudaStream_t aux = nullptr; std::vector<cudaEvent_t> ev; };
-std::mutex g_la_mutex;
-std::map<cudaStream_t, LookaheadCtx> g_la;      // one auxiliary stream + event pool per calling stream
-LookaheadCtx *lookahead_ctx(cudaStream_t st, size_t n_events) {
-    std::lock_guard<std::mutex> lock(g_la_mutex);
-    LookaheadCtx &c = g_la[st];
-    if (c.aux == nullptr) {
-        int prio = 0;
-        if (cudaStreamGetPriority(st, &prio) != cudaSuccess) prio = 0;
-        if (cudaStreamCreateWithPriority(&c.aux, cudaStreamNonBlocking, prio) != cudaSuccess) return nullptr;
-    }
-    while (c.ev.size() < n_events) {
-        cudaEvent_t e;
-        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        c.ev.push_back(e);
-    }
-    return &c;
-}
-int prepare_diag_variant() {      // GQ_DIAG_V2: 0 = chol_diag_kernel, 1 (default) = chol_diag_v2_kernel, 3 = experimental chol_diag_v3.cuh
-    const char *e = getenv("GQ_DIAG_V2");      // read on every call: tests and micro-benchmarks flip it at run time
-    return (e && e[0] == '0') ? 0 : (e && e[0] == '3') ? 3 : 1;
+int prepare_diag_variant() {      // GQ_DIAG_V2: 0 = chol_diag_kernel, 1 = chol_diag_v2_kernel, 3 = register-resident chol_diag_v3.cuh,
+    const char *e = getenv("GQ_DIAG_V2");      // 4 (default) = two-level chol_diag_v4.cuh; read on every call (tests / micro-benchmarks)
+    return (e && e[0] == '0') ? 0 : (e && e[0] == '1') ? 1 : (e && e[0] == '3') ? 3 : 4;
 }
 // GQ_PREPARE_GEMM=tf32|f16 (read on every call: tests and micro-benchmarks flip it): which tcgen05 GEMM the chain uses --
 // 3xTF32 (gemm_tf32.cu) or split-fp16 (gemm_f16x3.cu: half the operand bytes, twice the MMA rate, same 22-bit operands).
@@ -291,8 +273,7 @@ bool prepare_use_simt() {
 
 extern "C" size_t gq_prepare_workspace_bytes(int d_col) {
     const size_t n = (size_t)d_col;
-    return 3 * n * n * sizeof(float) + (n + 64) * sizeof(int) + 1024 + split_ws_bytes(n) +
-           (prepare_lookahead() ? split_ws_bytes(n) + 1024 : 0);
+    return 3 * n * n * sizeof(float) + (n + 64) * sizeof(int) + 1024 + split_ws_bytes(n);
 }
 
 extern "C" int gq_prepare(float *H, const float *W, int d_row, int d_col, float rel_damp, float *U_out, void *workspace,
@@ -337,29 +318,30 @@ extern "C" int gq_prepare(float *H, const float *W, int d_row, int d_col, float 
     const int diag_variant = prepare_diag_variant();
     if (diag_variant == 3)
         GQ_CHECK_CUDA(cudaFuncSetAttribute(cd3::chol_diag_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cd3::Smem3)));
-    auto tc_gemm_on = [&](cudaStream_t stream_, void *ws_, const float *Ap, const float *Bp, float *Cp, int M, int N, int K, int batch,
-                          long ab, long bb, long cb, float alpha, float beta, int tile_mode, int k_mode, bool same) {
+    if (diag_variant == 4)
+        GQ_CHECK_CUDA(cudaFuncSetAttribute(cd4::chol_diag_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cd4::Smem4)));
+    auto tc_gemm = [&](const float *Ap, const float *Bp, float *Cp, int M, int N, int K, int batch, long ab, long bb, long cb,
+                       float alpha, float beta, int tile_mode, int k_mode, bool same) {
         tg::GemmArgs g;
         g.A = Ap; g.lda = ld; g.a_batch = ab; g.B = Bp; g.ldb = ld; g.b_batch = bb; g.C = Cp; g.ldc = ld; g.c_batch = cb;
         g.M = M; g.N = N; g.K = K; g.batch = batch; g.alpha = alpha; g.beta = beta; g.tile_mode = tile_mode; g.k_mode = k_mode;
         g.same_ab = same;
-        return use_f16 ? th::gemm_f16x3_nt(g, ws_, sws_bytes, stream_) : tg::gemm_tf32x3_nt(g, ws_, sws_bytes, stream_);
+        return use_f16 ? th::gemm_f16x3_nt(g, sws, sws_bytes, st) : tg::gemm_tf32x3_nt(g, sws, sws_bytes, st);
     };
-    auto tc_gemm = [&](const float *Ap, const float *Bp, float *Cp, int M, int N, int K, int batch, long ab, long bb, long cb,
-                       float alpha, float beta, int tile_mode, int k_mode, bool same) {
-        return tc_gemm_on(st, sws, Ap, Bp, Cp, M, N, K, batch, ab, bb, cb, alpha, beta, tile_mode, k_mode, same);
-    };
-    // look-ahead (experimental, see prepare_lookahead): auxiliary stream, second split workspace, 2 events per step
-    LookaheadCtx *la = nullptr;
-    void *sws2 = nullptr;
-    if (!simt && n >= 8192 && prepare_lookahead() && ws_bytes >= gq_prepare_workspace_bytes(d_col)) {
-        la = lookahead_ctx(st, 2 * (size_t)(n / NB) + 2);
-        sws2 = (void *)(((uintptr_t)sws + sws_bytes + 1023) & ~(uintptr_t)1023);
-    }
-    int la_prev_b = -1;      // index of the event recorded after the previous step's rest-of-trailing update
+    const int G = simt ? 1 : prepare_group();
     for (int k0 = 0; k0 < n; k0 += NB) {
+        const int g0 = (k0 / NB) / G * G * NB;                 // first column of this step's group
+        int rc = GQ_OK;
+        if (k0 > g0) {
+            // left-looking inside the group: block column k0 (diagonal block included) receives the group's earlier columns
+            //   A[k0:, k0:k0+128] -= L[k0:, g0:k0] L[k0:k0+128, g0:k0]^T
+            const float *Lg = A + (size_t)k0 * ld + g0;
+            rc = tc_gemm(Lg, Lg, A + (size_t)k0 * ld + k0, n - k0, NB, k0 - g0, 1, 0, 0, 0, -1.0f, 1.0f, tg::TM_FULL, tg::KM_FULL, false);
+            if (rc) return rc;
+        }
         if (diag_variant == 1) chol_diag_v2_kernel<<<1, DT2, sizeof(DiagSmem2), st>>>(A, Li, simt ? nullptr : LiT, ld, k0, flag);
         else if (diag_variant == 3) cd3::chol_diag_v3_kernel<<<1, cd3::T3, sizeof(cd3::Smem3), st>>>(A, Li, simt ? nullptr : LiT, ld, k0, flag);
+        else if (diag_variant == 4) cd4::chol_diag_v4_kernel<<<1, cd4::T4, sizeof(cd4::Smem4), st>>>(A, Li, simt ? nullptr : LiT, ld, k0, flag);
         else chol_diag_kernel<<<1, DT, sizeof(DiagSmem), st>>>(A, Li, simt ? nullptr : LiT, ld, k0, flag);
         gq_count_launches(1);
         const int rem = n - k0 - NB;
@@ -367,7 +349,6 @@ extern "C" int gq_prepare(float *H, const float *W, int d_row, int d_col, float 
             float *P = A + (size_t)(k0 + NB) * ld + k0;          // panel (rem x 128)
             const float *Lkk_inv = Li + (size_t)k0 * ld + k0;     // inv(L_kk), row-major lower
             float *T = A + (size_t)(k0 + NB) * ld + (k0 + NB);    // trailing matrix
-            int rc;
             if (simt) {
                 // P <- P * inv(L_kk)^T : A(m,k) = P[m][k], B(k,n) = Lkk_inv[n][k]
                 rc = sg::launch(gemm_args(P, ld, 1, Lkk_inv, 1, ld, P, ld, rem, NB, NB, 1.0f, 0.0f, sg::TM_FULL, sg::KM_FULL), 1, st);
@@ -377,33 +358,16 @@ extern "C" int gq_prepare(float *H, const float *W, int d_row, int d_col, float 
                 // both GEMMs are NT (K-contiguous operands); operands are copied (split) before C is written => in place is safe
                 rc = tc_gemm(P, Lkk_inv, P, rem, NB, NB, 1, 0, 0, 0, 1.0f, 0.0f, tg::TM_FULL, tg::KM_FULL, false);
                 if (rc) return rc;
-                if (la != nullptr && rem > NB) {
-                    const int step = k0 / NB;
-                    cudaEvent_t ev_panel = la->ev[2 * step], ev_b = la->ev[2 * step + 1];
-                    GQ_CHECK_CUDA(cudaEventRecord(ev_panel, st));
-                    GQ_CHECK_CUDA(cudaStreamWaitEvent(la->aux, ev_panel, 0));
-                    // the next block column received the previous step's rest-of-trailing update on the auxiliary stream
-                    if (la_prev_b >= 0) GQ_CHECK_CUDA(cudaStreamWaitEvent(st, la->ev[la_prev_b], 0));
-                    // (A) next block column, on the chain's stream:  T[:, 0:128] -= P * P[0:128]^T
-                    rc = tc_gemm(P, P, T, rem, NB, NB, 1, 0, 0, 0, -1.0f, 1.0f, tg::TM_FULL, tg::KM_FULL, false);
-                    if (rc) return rc;
-                    // (B) the rest, on the auxiliary stream:  T[128:, 128:] -= P[128:] P[128:]^T  (lower tiles)
-                    const float *P2 = P + (size_t)NB * ld;
-                    float *T2 = T + (size_t)NB * ld + NB;
-                    rc = tc_gemm_on(la->aux, sws2, P2, P2, T2, rem - NB, rem - NB, NB, 1, 0, 0, 0, -1.0f, 1.0f, tg::TM_LOWER, tg::KM_FULL, true);
-                    if (rc) return rc;
-                    GQ_CHECK_CUDA(cudaEventRecord(ev_b, la->aux));
-                    la_prev_b = 2 * step + 1;
-                } else {
-                    if (la_prev_b >= 0) { GQ_CHECK_CUDA(cudaStreamWaitEvent(st, la->ev[la_prev_b], 0)); la_prev_b = -1; }
-                    rc = tc_gemm(P, P, T, rem, rem, NB, 1, 0, 0, 0, -1.0f, 1.0f, tg::TM_LOWER, tg::KM_FULL, true);   // T -= P P^T
+                if (k0 + NB == g0 + G * NB) {
+                    // the group is complete: everything behind it gets the group's G block columns at once
+                    //   T -= L[ge:, g0:ge] L[ge:, g0:ge]^T      (lower tiles)
+                    const float *Lg = A + (size_t)(k0 + NB) * ld + g0;
+                    rc = tc_gemm(Lg, Lg, T, rem, rem, k0 + NB - g0, 1, 0, 0, 0, -1.0f, 1.0f, tg::TM_LOWER, tg::KM_FULL, true);
                 }
             }
             if (rc) return rc;
         }
     }
-
-    if (la_prev_b >= 0) GQ_CHECK_CUDA(cudaStreamWaitEvent(st, la->ev[la_prev_b], 0));    // look-ahead: join the auxiliary stream
 
     // --- X = inv(L) by pairwise merging of diagonal blocks:  X21 = -X22 * L21 * X11.  U_out is the scratch. ---
     // Tensor path keeps Y = X^T as well so that every product is NT:

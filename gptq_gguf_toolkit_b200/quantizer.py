@@ -120,7 +120,7 @@ class Quantizer:
                  calibration_batch_size: int = 8, share_hessians: bool = True, keep_results: bool = False,
                  save_packed: bool = True, timer: Optional[PhaseTimer] = None, early_exit_pass1: bool = True,
                  overlap_prepare: bool = True, defer_last_layer: bool = True, fused_forward_ops: bool = True,
-                 early_prepare: bool = True, rtn_native_arith: bool = True) -> None:
+                 early_prepare: bool = True, rtn_native_arith: bool = True, shard_prepare: bool = True) -> None:
         self.model = model
         self.data_loader = data_loader
         self.quantizable_modules = quantizable_modules
@@ -146,6 +146,10 @@ class Quantizer:
         # embed_tokens / lm_head of a 16-bit model: scale search in the weight's own arithmetic like the reference
         # (quantizer.py:303-305 -> gq_rtn_quantize_native); False = weights widened to fp32
         self.rtn_native_arith = rtn_native_arith
+        # several ranks: every Cholesky chain (gq_prepare) of a block runs on ONE owner rank and U is broadcast, instead of
+        # every rank running all of them (the reference factors on every rank too, gptq.py:305-324 is not rank-guarded)
+        self.shard_prepare = shard_prepare
+        self._bcast_groups: dict = {}
         self.fused_installed: List[str] = []
         self._split_ok: Optional[bool] = None
         self._side_streams: list = []
@@ -298,6 +302,49 @@ class Quantizer:
             groups.setdefault(id(h.hessian), []).append(name)
         return list(groups.values())
 
+    def _chain_owner(self, gi: int, handles: Dict[str, GPTQ]) -> int:
+        """Owner rank of group gi's Cholesky chain: the chains of a block (cost ~ d_col^3) are dealt out greedily, most
+        expensive first, to the least loaded rank -- counting ranks from the LAST one down, because rank 0 also moves the
+        results to the host and writes the files.  Deterministic, so every rank computes the same assignment."""
+        world = _world()
+        groups = self._group_names(handles)
+        cost = [float(handles[g[0]].d_col) ** 3 for g in groups]
+        load = [0.0] * world
+        owner = [0] * len(groups)
+        for g in sorted(range(len(groups)), key=lambda i: (-cost[i], i)):
+            r = min(range(world - 1, -1, -1), key=lambda k: (load[k], -k))
+            owner[g] = r
+            load[r] += cost[g]
+        return owner[gi]
+
+    def _bcast_group(self, gi: int):
+        """One process group (NCCL communicator) per chain slot: a broadcast of U waits for its chain on the side stream,
+        and collectives of one communicator execute in issue order -- on the default group the short chains' results and
+        the all-gathers would queue behind the longest chain."""
+        if gi not in self._bcast_groups:
+            self._bcast_groups[gi] = dist.new_group(ranks=list(range(_world())))
+        return self._bcast_groups[gi]
+
+    def _prepare_or_receive(self, gi: int, handles, H, W, rel_damp, side, slot):
+        """gq_prepare on the chain's owner rank + broadcast of (U, not-PD flag) on the chain's stream; plain ops.prepare with
+        one rank or shard_prepare off."""
+        if not (_dist_on() and self.shard_prepare):
+            return ops.prepare(H, W, rel_damp, stream=side, slot=slot)
+        owner = self._chain_owner(gi, handles)
+        grp = self._bcast_group(gi)
+        if _rank() == owner:
+            U, flag = ops.prepare(H, W, rel_damp, stream=side, slot=slot)
+        else:
+            U = torch.empty(H.shape[0], H.shape[0], dtype=torch.float32, device=H.device)
+            flag = torch.zeros(1, dtype=torch.int32, device=H.device)
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream(H.device))
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            with self.timer.span("bcast_u"):
+                dist.broadcast(U, src=owner, group=grp)
+                dist.broadcast(flag, src=owner, group=grp)
+        return U, flag
+
     def _plan_group(self, gi: int, names: List[str], handles: Dict[str, GPTQ], quant_config, overlap: bool):
         """Phase A of one group (quantizer.py:242-255 up to the factor): all-reduce of H, stacked fp32 working copy,
         dead-channel fix, Cholesky chain (on side stream `gi` when `overlap`).  Returns the plan tuple consumed by
@@ -341,7 +388,8 @@ class Quantizer:
                 U_perm, flag = ops.prepare(Hp, Wp, kw.get("rel_damp", 1e-2), stream=side, slot=1 + gi if overlap else 0)
                 not_pd.append(flag)
             if perm is None or any(q3):
-                U, flag = ops.prepare(acc.H, W, kw.get("rel_damp", 1e-2), stream=side, slot=1 + gi if overlap else 0)  # gptq.py:305-324
+                U, flag = self._prepare_or_receive(gi, handles, acc.H, W, kw.get("rel_damp", 1e-2), side,
+                                                   1 + gi if overlap else 0)                               # gptq.py:305-324
                 not_pd.append(flag)
             done = None
             if side is not None:

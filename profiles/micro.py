@@ -62,29 +62,16 @@ def main():
         for n in (4096, 14336):
             H0 = spd(n)
             W = torch.randn(256, n, device="cuda")
-            for v in ("1", "0") + (("3",) if "experimental" in what else ()):   # v2 (default), the original, experimental v3
-                os.environ["GQ_DIAG_V2"] = v
-                l0 = ops.launch_count()
+            l0 = ops.launch_count()
+            mn, av = timed(lambda: ops.prepare(H0.clone(), W, 0.01), warm=1, it=2)
+            print(f"prepare n={n} defaults (f16 GEMM, diag v4, group 4): {mn:.2f} ms (avg {av:.2f}), launches/call {(ops.launch_count() - l0) // 3}", flush=True)
+            for be, dv, grp in (("f16", "4", "1"), ("f16", "4", "2"), ("f16", "4", "8"), ("f16", "3", "4"), ("f16", "1", "4"), ("tf32", "4", "4"),
+                                ("tf32", "1", "1")):      # tcgen05 GEMM back-end, diagonal-block kernel, steps per trailing update
+                os.environ.update(GQ_PREPARE_GEMM=be, GQ_DIAG_V2=dv, GQ_PREPARE_GROUP=grp)
                 mn, av = timed(lambda: ops.prepare(H0.clone(), W, 0.01), warm=1, it=2)
-                print(f"prepare n={n} GQ_DIAG_V2={v}: {mn:.2f} ms (avg {av:.2f}), launches/call {(ops.launch_count() - l0) // 3}", flush=True)
-            os.environ["GQ_DIAG_V2"] = "1"
-            for be in ("tf32", "f16"):      # tcgen05 GEMM back-end of the chain
-                os.environ["GQ_PREPARE_GEMM"] = be
-                for v in ("1", "3"):
-                    os.environ["GQ_DIAG_V2"] = v
-                    mn, av = timed(lambda: ops.prepare(H0.clone(), W, 0.01), warm=1, it=2)
-                    print(f"prepare n={n} GQ_PREPARE_GEMM={be} GQ_DIAG_V2={v}: {mn:.2f} ms (avg {av:.2f})", flush=True)
-            os.environ.pop("GQ_PREPARE_GEMM", None)
-            os.environ["GQ_DIAG_V2"] = "1"
-            if "experimental" in what and n >= 8192:      # look-ahead Cholesky (GQ_PREPARE_LOOKAHEAD=1), checked against the default U
-                Hc = H0.clone(); U_ref, _ = ops.prepare(Hc, W, 0.01)
-                os.environ["GQ_PREPARE_LOOKAHEAD"] = "1"
-                Hc = H0.clone(); U_la, _ = ops.prepare(Hc, W, 0.01)
-                torch.cuda.synchronize()
-                print(f"prepare n={n} look-ahead: max |U - U_default| / max|U| = {float((U_la - U_ref).abs().max() / U_ref.abs().max()):.2e}", flush=True)
-                mn, av = timed(lambda: ops.prepare(H0.clone(), W, 0.01), warm=1, it=2)
-                print(f"prepare n={n} GQ_PREPARE_LOOKAHEAD=1: {mn:.2f} ms (avg {av:.2f})", flush=True)
-                os.environ["GQ_PREPARE_LOOKAHEAD"] = "0"
+                print(f"prepare n={n} GQ_PREPARE_GEMM={be} GQ_DIAG_V2={dv} GQ_PREPARE_GROUP={grp}: {mn:.2f} ms (avg {av:.2f})", flush=True)
+            for k in ("GQ_PREPARE_GEMM", "GQ_DIAG_V2", "GQ_PREPARE_GROUP"):
+                os.environ.pop(k, None)
     if "hessian" in what:
         for n, T in ((4096, 16384), (14336, 16384)):
             X = torch.randn(T, n, device="cuda").to(torch.bfloat16)
@@ -122,10 +109,6 @@ def main():
             for name, mode in (("auto", 0), ("left", 2), ("right", 3)):
                 mn, _ = timed(lambda: ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16, mode=mode), warm=1, it=2)
                 res[name] = mn
-            if "experimental" in what:      # exact_update_v2_kernel (GQ_UPDATE_V2=1, read by the library on every launch)
-                os.environ["GQ_UPDATE_V2"] = "1"
-                res["right+update_v2"], _ = timed(lambda: ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16, mode=3), warm=1, it=2)
-                os.environ["GQ_UPDATE_V2"] = "0"
             print(f"schedules {rows}x{n}: " + ", ".join(f"{k} {v:.2f} ms" for k, v in res.items()), flush=True)
             del U, W0
     if "rtn" in what:

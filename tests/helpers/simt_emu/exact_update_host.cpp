@@ -1,4 +1,4 @@
-// TEST-ONLY: gptq_gguf_toolkit_b200/csrc/exact_update_v2.cuh (an experimental kernel that has not run on a GPU yet) on the SIMT
+// TEST-ONLY: the trailing-update kernel body of the exact right-looking schedule (csrc/rank_update.cuh) on the SIMT
 // emulator.  cp.async is emulated AS LATE AS LEGAL: a copy is only performed when a cp_async_wait<N> of the issuing thread
 // retires its group (all but the newest N committed groups), so that reading a pipeline stage before the wait that covers it
 // -- or waiting for too few groups -- shows up as stale data and a bit mismatch.
@@ -29,23 +29,14 @@ static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b
 static inline float __fsub_rn(float a, float b) { return a - b; }
 alignas(16) unsigned char smem_raw[80 * 1024];       // the kernel's `extern __shared__ ... smem_raw[]`
 #include "rank_update.cuh"          // the SHIPPED trailing-update body (exact_update_kernel) and rank_update<>
-#include "exact_update_v2.cuh"
-
-extern "C" int run_exact_update_v2(float *W, const float *U, int d_row, int d_col, int c) {
-    static_assert(upd2::SMEM_BYTES <= sizeof(smem_raw), "shared memory array too small");
-    const int nwin = (d_col - c - 256) / 256;
-    if (nwin <= 0) return 0;
-    upd2::Params p{W, U, d_row, d_col};
-    simt::launch(dim3(nwin, (d_row + upd2::R - 1) / upd2::R), dim3(upd2::NT2), [&]() { exact_update_v2_kernel(p, c); });
-    return 0;
-}
+namespace upd { struct Params { float *W; const float *U; int d_row, d_col; }; }
 
 // the shipped kernel: exact_update_kernel = exact_update_body<LayerParams> (csrc/gptq_layer.cu); 256 threads per CTA
 extern "C" int run_exact_update_v1(float *W, const float *U, int d_row, int d_col, int c) {
     static_assert((size_t)rk::S * (rk::US_FLOATS + rk::ES_FLOATS) * sizeof(float) <= sizeof(smem_raw), "shared memory array too small");
     const int nwin = (d_col - c - 256) / 256;
     if (nwin <= 0) return 0;
-    upd2::Params p{W, U, d_row, d_col};
+    upd::Params p{W, U, d_row, d_col};
     simt::launch(dim3(nwin, (d_row + rk::R - 1) / rk::R), dim3(rk::NT), [&]() { exact_update_body(p, c, smem_raw); });
     return 0;
 }

@@ -14,7 +14,7 @@ static inline uint32_t __float_as_uint(float x) { uint32_t u; std::memcpy(&u, &x
 static inline float __uint_as_float(uint32_t u) { float x; std::memcpy(&x, &u, 4); return x; }
 static inline long long clock64() { return 0; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
-// cp.async as late as legal (see exact_update_v2_host.cpp)
+// cp.async as late as legal (see exact_update_host.cpp)
 namespace cpa {
 struct Copy { void *dst; const void *src; int n; };
 struct Thread { std::vector<Copy> open; std::deque<std::vector<Copy>> groups; };

@@ -261,13 +261,14 @@ def _spd_problem(n, d_row, seed):
     return H, W
 
 
-_DIAG = [("1", "diag_v2"), ("0", "diag_v1")] + ([("3", "diag_v3_experimental")] if os.environ.get("GQ_TEST_EXPERIMENTAL") == "1" else [])
+_DIAG = [("4", "diag_v4"), ("3", "diag_v3"), ("1", "diag_v2"), ("0", "diag_v1")]
 
 
 @pytest.fixture(params=[v for v, _ in _DIAG], ids=[n for _, n in _DIAG])
 def diag_variant(request, monkeypatch):
-    """Both diagonal-block kernels of gq_prepare (csrc/linalg.cu: chol_diag_v2_kernel, the default, and the original
-    chol_diag_kernel) must meet the same B2 bounds; the library reads GQ_DIAG_V2 on every call."""
+    """All diagonal-block kernels of gq_prepare (csrc/linalg.cu: the two-level chol_diag_v4_kernel, the default since round 2,
+    the register-resident chol_diag_v3_kernel, chol_diag_v2_kernel and the original chol_diag_kernel) must meet the same B2 bounds; the library reads
+    GQ_DIAG_V2 on every call."""
     monkeypatch.setenv("GQ_DIAG_V2", request.param)
     return request.param
 

@@ -1,6 +1,7 @@
 """GPU: accuracy of gq_prepare (csrc/linalg.cu) at the sizes the Llama-3-8B benchmark runs -- n = 4096 (q/k/v/o, gate/up) and
 n = 14336 (down_proj) -- against an fp64 factorisation on the device (reference: gptq.py:305-324 + linalg_utils.py:8-12,
-U = chol(inv(H + damp I), upper)).  Both tcgen05 GEMM back-ends of the chain (GQ_PREPARE_GEMM = tf32 | f16) must meet the bounds.
+U = chol(inv(H + damp I), upper)).  Both tcgen05 GEMM back-ends of the chain (GQ_PREPARE_GEMM = f16 (default) | tf32) and the
+grouped / ungrouped trailing updates (GQ_PREPARE_GROUP) must meet the bounds.
 
 Bounds (fp32 factorisation of a matrix with cond ~ 1e3..1e4, the B2 class of DESIGN.md section 2):
   * max |U - U64| <= 2e-4 max|U64|           (same bound as the small-n test in test_gpu_parity.py)
@@ -35,10 +36,11 @@ def _problem(n, seed):
     return H, W
 
 
-@pytest.mark.parametrize("backend", ["tf32", "f16"])
+@pytest.mark.parametrize("backend,group", [("f16", "4"), ("f16", "1"), ("tf32", "4")])
 @pytest.mark.parametrize("n", [4096, 14336])
-def test_prepare_accuracy_at_llama_sizes(ops, n, backend, monkeypatch):
+def test_prepare_accuracy_at_llama_sizes(ops, n, backend, group, monkeypatch):
     monkeypatch.setenv("GQ_PREPARE_GEMM", backend)
+    monkeypatch.setenv("GQ_PREPARE_GROUP", group)      # block columns per trailing update of the Cholesky (csrc/linalg.cu)
     H, W = _problem(n, n)
     Hd = H.clone()
     U, flag = ops.prepare(Hd, W, 0.01)
@@ -51,6 +53,6 @@ def test_prepare_accuracy_at_llama_sizes(ops, n, backend, monkeypatch):
     R = U.double() @ H64 @ U.double().T
     R.diagonal().sub_(1.0)
     resid = float(R.abs().max())
-    print(f"gq_prepare n={n} backend={backend}: max|U-U64|/max|U64| = {rel:.2e}, max|U H U^T - I| = {resid:.2e}")
+    print(f"gq_prepare n={n} backend={backend} group={group}: max|U-U64|/max|U64| = {rel:.2e}, max|U H U^T - I| = {resid:.2e}")
     assert rel <= 2e-4, rel
     assert resid <= 2e-3, resid

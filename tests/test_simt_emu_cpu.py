@@ -1,7 +1,7 @@
 """Kernels written without GPU access, run on the host through a small SIMT emulator (tests/helpers/simt_emu: one fiber per
 CUDA thread, __syncthreads() = barrier between fibers) to catch indexing / algorithm mistakes before they cost GPU minutes.
-Covered: the diagonal-block kernels of gq_prepare -- the shipped chol_diag_v2.cuh and the experimental register-resident
-chol_diag_v3.cuh (GQ_DIAG_V2=3) --
+Covered: the diagonal-block kernels of gq_prepare -- chol_diag_v2.cuh, the register-resident chol_diag_v3.cuh and the two-level
+chol_diag_v4.cuh (GQ_DIAG_V2 = 1 / 3 / 4, the last one is the default) --
 (128 x 128 Cholesky factor + its inverse + the inverse's transpose, against a double-precision factorisation)."""
 import ctypes as C
 import os
@@ -25,6 +25,16 @@ def lib(tmp_path_factory):
 
 
 @pytest.fixture(scope="module")
+def lib_v4(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu") / "libchol_v4_emu.so")
+    cmd = ["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-x", "c++", "-I", EMU,
+           "-I", os.path.join(ROOT, "gptq_gguf_toolkit_b200", "csrc"), os.path.join(EMU, "chol_diag_v4_host.cpp"), "-o", so]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-4000:]
+    return C.CDLL(so)
+
+
+@pytest.fixture(scope="module")
 def lib_v2(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("emu") / "libchol_v2_emu.so")
     cmd = ["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-I", EMU,
@@ -34,9 +44,9 @@ def lib_v2(tmp_path_factory):
     return C.CDLL(so)
 
 
-@pytest.mark.parametrize("variant", ["v2_shipped", "v3_experimental"])
+@pytest.mark.parametrize("variant", ["v2", "v3", "v4_default"])
 @pytest.mark.parametrize("k0", [0, 128])
-def test_chol_diag_on_the_emulator(lib, lib_v2, k0, variant):
+def test_chol_diag_on_the_emulator(lib, lib_v2, lib_v4, k0, variant):
     rng = np.random.default_rng(k0 + 1)
     n, nb = 384, 128
     M = rng.standard_normal((nb, 3 * nb))
@@ -47,7 +57,7 @@ def test_chol_diag_on_the_emulator(lib, lib_v2, k0, variant):
     BinvT = np.full((n, n), 7.0, np.float32)
     flag = np.zeros(1, np.int32)
     p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
-    run = lib_v2.run_chol_diag_v2 if variant == "v2_shipped" else lib.run_chol_diag_v3
+    run = {"v2": lib_v2.run_chol_diag_v2, "v3": lib.run_chol_diag_v3, "v4_default": lib_v4.run_chol_diag_v4}[variant]
     run(p(A, C.c_float), p(Binv, C.c_float), p(BinvT, C.c_float), C.c_long(n), C.c_int(k0), p(flag, C.c_int))
     L = np.linalg.cholesky(H)
     X = np.linalg.inv(L)
@@ -69,18 +79,17 @@ def test_chol_diag_on_the_emulator(lib, lib_v2, k0, variant):
 def lib_upd(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("emu") / "libupd2_emu.so")
     cmd = ["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-I", EMU,
-           "-I", os.path.join(ROOT, "gptq_gguf_toolkit_b200", "csrc"), os.path.join(EMU, "exact_update_v2_host.cpp"), "-o", so]
+           "-I", os.path.join(ROOT, "gptq_gguf_toolkit_b200", "csrc"), os.path.join(EMU, "exact_update_host.cpp"), "-o", so]
     out = subprocess.run(cmd, capture_output=True, text=True)
     assert out.returncode == 0, out.stderr[-4000:]
     return C.CDLL(so)
 
 
-@pytest.mark.parametrize("kernel", ["run_exact_update_v1", "run_exact_update_v2"], ids=["shipped", "v2_experimental"])
+@pytest.mark.parametrize("kernel", ["run_exact_update_v1"], ids=["shipped"])
 @pytest.mark.parametrize("d_row,d_col,c", [(40, 1024, 256), (33, 768, 0), (64, 1280, 512)])
 def test_exact_update_on_the_emulator(lib_upd, d_row, d_col, c, kernel):
     """The SHIPPED trailing-update kernel body (csrc/rank_update.cuh: exact_update_body + rank_update<>, what
-    exact_update_kernel and the left-looking loop of gptq_layer_kernel execute) and the experimental
-    gptq_gguf_toolkit_b200/csrc/exact_update_v2.cuh (GQ_UPDATE_V2=1): the rank-256 trailing update of the exact schedule, W[:, c+256:] <- (W - chain(E[:, c:c+128], U[c:c+128, :])) - chain(E[:, c+128:c+256], U[c+128:c+256, :]) with
+    exact_update_kernel and the left-looking loop of gptq_layer_kernel execute): the rank-256 trailing update of the exact schedule, W[:, c+256:] <- (W - chain(E[:, c:c+128], U[c:c+128, :])) - chain(E[:, c+128:c+256], U[c+128:c+256, :]) with
     E = W[:, c:c+256], every chain a single-accumulator fp32 FMA chain in ascending k -- bit for bit against a plain
     restatement, ragged row count included; columns left of c+256 and rows must be untouched."""
     import math
