@@ -144,7 +144,7 @@ REFERENCE_MEASURED = {
 def cpu_reference_sample(w, threads: int):
     """Times a bounded sample (~30 s of CPU work) and extrapolates each phase by its algorithmic work to the whole model.
     Returns (whole_model_hot_path_seconds, detail).  Sample: 8 sequences of H.addmm_ and one Cholesky chain at every distinct
-    d_col, the column loop on WHOLE-WIDTH slabs (64 rows at the narrow width, 32 rows at the widest)."""
+    d_col, the column loop on WHOLE-WIDTH slabs (512 rows at the narrow width, 128 rows at the widest)."""
     from oracle import oracle as orc
     import numpy as np
     torch.set_num_threads(threads)
@@ -171,8 +171,8 @@ def cpu_reference_sample(w, threads: int):
     # 2. Cholesky chain, measured at every distinct d_col (gptq.py:305-324)
     t_p = {}
     for c in dcols:
-        x = torch.randn(2 * c, c, generator=g)
-        H = (x.T @ x) / c + 0.01 * torch.eye(c)
+        x = torch.randn(c // 4, c, generator=g)          # SPD, well conditioned; the factorisation's cost does not depend on the values
+        H = (x.T @ x) / c + 0.5 * torch.eye(c)
         t0 = time.perf_counter()
         Hi = torch.cholesky_inverse(torch.linalg.cholesky(H))
         torch.linalg.cholesky(Hi, upper=True)
@@ -184,7 +184,7 @@ def cpu_reference_sample(w, threads: int):
     #    on a slab of the layer's FULL width at every distinct d_col
     t_row = {}
     for c in dcols:
-        rows = 64 if c <= 4096 else 32
+        rows = 512 if c <= 4096 else 128
         rng = np.random.default_rng(c)
         W = (rng.standard_normal((rows, c)) * 0.02).astype(np.float32)
         U = np.triu(rng.standard_normal((c, c)).astype(np.float32) * 0.01) + np.eye(c, dtype=np.float32)
@@ -201,7 +201,7 @@ def cpu_reference_sample(w, threads: int):
 
 
 CPU_SAMPLE_NOTE = ("per phase: H.addmm_ of 8 sequences of 2048 tokens at each d_col, one Cholesky chain (cholesky, cholesky_inverse, "
-                   "cholesky upper) at each d_col, the column loop on whole-width slabs (64 rows x 4096, 32 rows x 14336); scaled by "
+                   "cholesky upper) at each d_col, the column loop on whole-width slabs (512 rows x 4096, 128 rows x 14336); scaled by "
                    "algorithmic work to 32 blocks x 7 projections x 128 sequences -- EXTRAPOLATED, hot path only (no model forwards, "
                    "no embed/lm_head), oracle PORT of the reference (see reference_measured for the reference's own functions)")
 
@@ -261,7 +261,10 @@ def main():
     ap.add_argument("--qtype", type=str, default="Q4_K")
     ap.add_argument("--batch", type=int, default=8, help="calibration sequences per block forward")
     ap.add_argument("--mode", type=str, default="both", choices=["exact", "fast", "both"],
-                    help="exact: bit-identical fp32 rank-k (headline); fast: tcgen05 3xTF32 rank-k; both: headline exact + one fast step")
+                    help="exact: bit-identical fp32 rank-k (headline); fast: tcgen05 split-fp16 rank-k; both: headline exact + one fast step")
+    ap.add_argument("--bit-width-configuration", type=str, default=None,
+                    help="JSON file {projection name: Q2_K..Q6_K} (the reference's --bit_width_configuration, quant.py:203-217); "
+                         "BASELINE.json configs[2]: profiles/configs/mixed_q2k_q6k.json")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="ablation: Cholesky chains on the main stream")
     ap.add_argument("--overlap", type=str, default="eager", choices=["eager", "staged"],
@@ -297,7 +300,9 @@ def main():
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     model = build_model(w, device)
-    quant_config = build_quant_config(args.qtype, None)
+    quant_config = build_quant_config(args.qtype, args.bit_width_configuration)
+    qdesc = f"uniform {args.qtype}" if args.bit_width_configuration is None else \
+        "mixed " + ", ".join(f"{k}:{v.name}" for k, v in sorted(quant_config.items()))
     names = [n for n, m in model.named_modules() if isinstance(m, torch.nn.Linear)] + ["model.embed_tokens"]
     mods = {n: model.get_submodule(n) for n in names}
     pristine = {n: m.weight.data.clone() for n, m in mods.items()}            # HBM copy (value runs)
@@ -312,6 +317,32 @@ def main():
             m.weight.data = pristine[n].clone()
 
     main_mode = "fast" if args.mode == "fast" else "exact"
+    checks = {}
+
+    def result_checksums(results):
+        """CRC-32 of the packed GGUF bytes of every module as they arrived in host memory (outside the timed region).
+        embed_tokens / lm_head (RTN, no calibration data) must be identical for every N; the GPTQ modules depend on the
+        rounding of the Hessian all-reduce (gptq.py:131-132 averages per-rank sums), so their bytes agree across N only
+        statistically -- in the reference as well."""
+        import zlib
+        per = {n: zlib.crc32(memoryview(o["packed"].numpy()).cast("B")) & 0xFFFFFFFF for n, o in results.items() if "packed" in o}
+        allc = 0
+        for n in sorted(per):
+            allc = zlib.crc32(per[n].to_bytes(4, "little"), allc)
+        return {"crc32_embed_tokens": per.get("model.embed_tokens"), "crc32_lm_head": per.get("lm_head"),
+                "crc32_block0_q_proj": per.get("model.layers.0.self_attn.q_proj"),
+                "crc32_of_all_module_crcs": allc & 0xFFFFFFFF, "modules": len(per)}
+
+    def weights_identical_on_all_ranks():
+        """After a step every rank's model holds the dequantised weights it was given by the all-gathers: compare an
+        order-independent 64-bit sum of the raw bits of every quantised module across the ranks."""
+        tot = torch.zeros(1, dtype=torch.int64, device=device)
+        for n, m in mods.items():
+            tot += m.weight.data.view(torch.int16).to(torch.int64).sum()
+        lo, hi = tot.clone(), tot.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        return bool((lo == hi).item())
 
     def one_step(e2e: bool, mode: str = None):
         timer = PhaseTimer(True)
@@ -351,6 +382,9 @@ def main():
         if e2e:
             for obj in q.results.values():
                 d2h += sum(v.numel() * v.element_size() for v in obj.values() if isinstance(v, torch.Tensor))
+            if rank == 0:
+                checks.clear()
+                checks.update(result_checksums(q.results))
             q.results.clear()
         bad = q.non_invertible_modules()
         return secs, timer.totals(), ops.launch_count() - l0, h2d, d2h, bad
@@ -435,7 +469,10 @@ def main():
             return {"value": None, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "unavailable": why}
         one_step(True)      # warm-up: fills torch's pinned-host cache with the result buffers (cudaHostAlloc is slow)
         secs, _, _, h2d, d2h, _ = one_step(True)
-        return {"value": secs, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": 1}
+        out = {"value": secs, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": 1}
+        if world > 1 and w["dtype"] != "float32":
+            out["weights_identical_on_all_ranks"] = weights_identical_on_all_ranks()
+        return out
 
     left = guarded("left-looking ablation", run_left) if (args.compare_left > 0 and main_mode == "exact") else None
     # e2e (a contract key) first; the fast-mode extra only on one GPU: it is an extra of the N = 1 line, and a rank-local
@@ -446,6 +483,9 @@ def main():
     if rank == 0:
         pk = peaks()
         rk_flops, hs_flops = algorithmic_work(w)
+        T_tok = w["n_seq"] * w["seq_len"]
+        # executed SYRK work: one Hessian per distinct input (q/k/v, o, gate/up, down), 128 x 256 tiles that touch the upper triangle
+        hs_exec = sum(2 * T_tok * c * c * (0.5 + 128.0 / c) for c in (w["hidden_size"], w["hidden_size"], w["hidden_size"], w["intermediate_size"])) * w["num_hidden_layers"]
         t_gptq = phases.get("gptq", 0.0)
         simt_peak = 148 * 128 * 2 * 1.965e9 / 1e12       # fp32 FFMA peak of the SIMT pipes at the max SM clock
         # flops of the launches of exact_update_kernel: sum over super-blocks of 2*d_row*256*(d_col - 256*(sb+1))
@@ -486,13 +526,17 @@ def main():
             "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: random-init {w['dtype']} Llama ({w['num_hidden_layers']} blocks, d_model {w['hidden_size']}), "
-                                   f"{w['n_seq']} calib seqs x {w['seq_len']}, uniform {args.qtype}, {main_mode} mode",
+                                   f"{w['n_seq']} calib seqs x {w['seq_len']}, {qdesc}, {main_mode} mode",
                        "calibration_batch": args.batch, "l2": "inputs (16 GB weights + 2 GB activations) exceed the 126 MB L2; no flush needed",
                        "parallelism": f"dp{world} over calibration sequences + row-sharded quantisation" if world > 1 else "single GPU"},
             "roofline": roofline,
             "phases_s": {k: round(v, 4) for k, v in sorted(phases.items())},
             "hot_path_s": round(hot, 4),
-            "hessian_tflops": round(hs_flops / world / phases["hessian"] / 1e12, 1) if phases.get("hessian") else None,
+            # the reference computes 7 full Hessians per block (2 T d_col^2 flops each); this build executes 4 (shared inputs),
+            # upper-triangle tiles only
+            "hessian_algorithmic_tflops": round(hs_flops / world / phases["hessian"] / 1e12, 1) if phases.get("hessian") else None,
+            "hessian_executed_tflops": round(hs_exec / world / phases["hessian"] / 1e12, 1) if phases.get("hessian") else None,
+            "hessian_executed_frac_of_peak": round(hs_exec / world / phases["hessian"] / 1e12 / pk["tf"], 3) if phases.get("hessian") else None,
             "gpu_launches": launches,
             "clocks": clocks,
             "non_invertible_modules": bad,
@@ -507,17 +551,29 @@ def main():
             tfs = gemm_flops / (pr["rankk_gemm_ms"] * 1e-3) / 1e12 if pr["rankk_gemm_ms"] > 0 else 0.0
             line["fast_mode"] = {
                 "value": secs_f, "unit": "s", "phases_s": {k: round(v, 4) for k, v in sorted(ph_f.items())},
-                "note": "GQ_MODE_FAST: rank-k updates between 256-column super-blocks as tcgen05 3xTF32 GEMMs (TMA-fed, TMEM "
-                        "accumulators); fp32-class accuracy, not bit-identical to the reference (tests: objective within 2e-3)",
+                "note": "GQ_MODE_FAST: the rank-k updates between 256-column super-blocks run as tcgen05 split-fp16 GEMMs "
+                        "(csrc/gemm_f16x3.cu: TMA-fed, 128x256 tiles, TMEM double-buffered, three kind::f16 MMAs per product on "
+                        "hi/lo operand pairs = 22-bit operands, fp32 accumulation); groups of 2 super-blocks share one trailing "
+                        "update (K = 512).  fp32-class accuracy, not bit-identical to the reference (tests: objective within 2e-3)",
                 "roofline": {"bound": "tensor", "achieved": tfs, "peak": pk["tf"], "unit": "TFLOP/s", "frac": tfs / pk["tf"],
-                             "traffic": None, "kernel": "gemm_tf32x3_kernel (rank-256 update, 3 TF32 MMAs per product)",
+                             "traffic": 265.8e6,
+                             "traffic_note": "ncu --set full of ONE launch (profiles/r02/r02b_ncu_details_gemm_f16x3_kernel.csv: down_proj "
+                                             "shape, 148 CTAs, 94.7 us): 172.4 MB read + 93.4 MB written; tensor pipe 72.7 % of active cycles",
+                             "kernel": "gemm_f16x3_kernel<256> (rank-256/512 trailing update, 3 fp16 MMAs per product)",
                              "launches": pr["rankk_gemm_launches"], "total_ms": pr["rankk_gemm_ms"],
-                             "executed_tf32_tflops": 3 * tfs,
-                             "hbm_note": "right-looking k=256: 64 flop/B => ~420 TFLOP/s HBM ceiling at 6.5 TB/s"},
+                             "avg_launch_ms": pr["rankk_gemm_ms"] / max(1, pr["rankk_gemm_launches"]),
+                             "algorithmic_flops_per_step": gemm_flops,
+                             "executed_fp16_tflops": 3 * tfs, "executed_frac_of_peak": 3 * tfs / pk["tf"],
+                             "peak_source": pk["source"]},
+                "operand_split_ms": pr.get("split_ms"), "operand_split_launches": pr.get("split_launches"),
                 "panel_kernel_ms": pr["panel_ms"], "panel_kernel_launches": pr["panel_launches"],
             }
         if e2e is not None:
             line["e2e"] = e2e
+            if checks:
+                line["checksums"] = dict(checks, note="CRC-32 of the packed GGUF bytes per module, from the e2e step's host copies; "
+                                         "the RTN modules (embed_tokens, lm_head) are N-independent, the GPTQ modules depend on the "
+                                         "rounding of the Hessian all-reduce (B3 class, as in the reference)")
 
         cpu = None
         if world == 1 and not args.no_cpu_baseline:

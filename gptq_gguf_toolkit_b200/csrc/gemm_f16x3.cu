@@ -255,6 +255,9 @@ __device__ __forceinline__ void split_f16(float xs, __half &hi, __half &lo) {
 }
 
 // One warp per (batch, row): max |x| over the row, then hi / lo of x * 2^e in the interleaved layout.
+// VEC: the row (K <= 1024, K % 4 == 0, 16-byte aligned) is read ONCE with 16-byte loads and stays in registers between the
+// two passes; the outputs go out as 8-byte stores (4 hi resp. 4 lo halves per lane).
+template <bool VEC>
 __global__ void __launch_bounds__(256) split_rows_f16_kernel(const float *__restrict__ src, long ld, long batch_stride, int rows,
                                                             int rows_pad, int K, int Kp, int batch, __half *__restrict__ dst,
                                                             float *__restrict__ scale) {
@@ -270,6 +273,37 @@ __global__ void __launch_bounds__(256) split_rows_f16_kernel(const float *__rest
             continue;
         }
         const float *s = src + b * batch_stride + (long)r * ld;
+        if (VEC) {
+            float4 v[8];
+            float mx = 0.0f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int k = 4 * (lane + 32 * t);
+                v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < K) v[t] = *reinterpret_cast<const float4 *>(s + k);
+                mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[t].x), fabsf(v[t].y))), fmaxf(fabsf(v[t].z), fabsf(v[t].w)));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            float sc, inv;
+            row_scale(mx, sc, inv);
+            if (lane == 0) scale[w] = inv;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int k = 4 * (lane + 32 * t);
+                if (k < Kp) {
+                    __half h[4], l[4];
+                    split_f16(__fmul_rn(v[t].x, sc), h[0], l[0]);
+                    split_f16(__fmul_rn(v[t].y, sc), h[1], l[1]);
+                    split_f16(__fmul_rn(v[t].z, sc), h[2], l[2]);
+                    split_f16(__fmul_rn(v[t].w, sc), h[3], l[3]);
+                    __half *o = d + 64 * (k >> 5) + (k & 31);
+                    *reinterpret_cast<uint2 *>(o) = *reinterpret_cast<const uint2 *>(h);
+                    *reinterpret_cast<uint2 *>(o + 32) = *reinterpret_cast<const uint2 *>(l);
+                }
+            }
+            continue;
+        }
         float mx = 0.0f;
         for (int k = lane; k < K; k += 32) mx = fmaxf(mx, fabsf(s[k]));
 #pragma unroll
@@ -362,7 +396,11 @@ namespace th {
 
 int split_rows_f16(const float *src, long ld, long batch_stride, int rows, int rows_pad, int K, int Kp, int batch, __half *dst,
                    float *scale, cudaStream_t st) {
-    split_rows_f16_kernel<<<ew_grid_rows((long)batch * rows_pad), 256, 0, st>>>(src, ld, batch_stride, rows, rows_pad, K, Kp, batch, dst, scale);
+    const bool vec = K <= 1024 && K % 4 == 0 && ld % 4 == 0 && batch_stride % 4 == 0 && ((uintptr_t)src % 16) == 0;
+    if (vec)
+        split_rows_f16_kernel<true><<<ew_grid_rows((long)batch * rows_pad), 256, 0, st>>>(src, ld, batch_stride, rows, rows_pad, K, Kp, batch, dst, scale);
+    else
+        split_rows_f16_kernel<false><<<ew_grid_rows((long)batch * rows_pad), 256, 0, st>>>(src, ld, batch_stride, rows, rows_pad, K, Kp, batch, dst, scale);
     gq_count_launches(1);
     GQ_CHECK_CUDA(cudaGetLastError());
     return GQ_OK;
@@ -421,6 +459,10 @@ int gemm_f16x3_nt(const tg::GemmArgs &g, void *ws, size_t ws_bytes, cudaStream_t
         gq_set_error("gemm_f16x3_nt: TM_LOWER needs M == N");
         return GQ_ERR_INVALID;
     }
+    if (g.same_ab && (g.N > g.M || g.batch != 1) && g.N != g.M) {      // same_ab: B = the first N rows of A (N == M: SYRK)
+        gq_set_error("gemm_f16x3_nt: same_ab needs N <= M (B is a row prefix of A) and, for N < M, batch == 1");
+        return GQ_ERR_INVALID;
+    }
     if (ws == nullptr || ws_bytes < workspace_bytes(g.M, g.N, g.K, g.batch, g.same_ab)) {
         gq_set_error("gemm_f16x3_nt: workspace too small");
         return GQ_ERR_WORKSPACE;
@@ -444,7 +486,7 @@ int gemm_f16x3_nt(const tg::GemmArgs &g, void *ws, size_t ws_bytes, cudaStream_t
     CUtensorMap ma, mb;
     const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     bool ok = make_map_2d(&ma, a16, dt, 2, (uint64_t)g.batch * g.M, (uint64_t)2 * Kp, 64, BM) &&
-              make_map_2d(&mb, b16, dt, 2, (uint64_t)g.batch * g.N, (uint64_t)2 * Kp, 64, wide ? 256 : 128);
+              make_map_2d(&mb, b16, dt, 2, (uint64_t)g.batch * (g.same_ab ? g.M : g.N), (uint64_t)2 * Kp, 64, wide ? 256 : 128);
     if (!ok) {
         gq_set_error("gemm_f16x3_nt: cuTensorMapEncodeTiled failed");
         return GQ_ERR_CUDA;

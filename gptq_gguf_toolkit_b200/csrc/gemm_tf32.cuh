@@ -21,7 +21,7 @@ struct GemmArgs {
     int M, N, K, batch;
     float alpha, beta;
     int tile_mode, k_mode;
-    bool same_ab;                             // B is A (SYRK): the operand is split once
+    bool same_ab;                             // B is A (SYRK): the operand is split once; gemm_f16x3_nt also takes N < M (B = A's first N rows)
 };
 
 // An operand whose hi / lo parts already exist: (rows x pitch) fp32 arrays; the block used starts at (row0, k0).

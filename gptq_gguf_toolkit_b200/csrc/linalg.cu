@@ -336,7 +336,8 @@ extern "C" int gq_prepare(float *H, const float *W, int d_row, int d_col, float 
             // left-looking inside the group: block column k0 (diagonal block included) receives the group's earlier columns
             //   A[k0:, k0:k0+128] -= L[k0:, g0:k0] L[k0:k0+128, g0:k0]^T
             const float *Lg = A + (size_t)k0 * ld + g0;
-            rc = tc_gemm(Lg, Lg, A + (size_t)k0 * ld + k0, n - k0, NB, k0 - g0, 1, 0, 0, 0, -1.0f, 1.0f, tg::TM_FULL, tg::KM_FULL, false);
+            // (B = the first 128 rows of A: with the fp16 back-end the operand is split once)
+            rc = tc_gemm(Lg, Lg, A + (size_t)k0 * ld + k0, n - k0, NB, k0 - g0, 1, 0, 0, 0, -1.0f, 1.0f, tg::TM_FULL, tg::KM_FULL, use_f16);
             if (rc) return rc;
         }
         if (diag_variant == 1) chol_diag_v2_kernel<<<1, DT2, sizeof(DiagSmem2), st>>>(A, Li, simt ? nullptr : LiT, ld, k0, flag);

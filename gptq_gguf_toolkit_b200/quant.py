@@ -3,7 +3,7 @@
 
     torchrun --nnodes=1 --nproc-per-node=$NUM_GPUS -m gptq_gguf_toolkit_b200.quant --model_name_or_path ... (see run_quant.sh)
 
-Extra flags: --calibration_batch_size, --random_init_config (build a random-init model from a config.json /
+Extra flags: --mode exact|fast, --calibration_batch_size, --random_init_config (build a random-init model from a config.json /
 LlamaConfig kwargs instead of loading weights; used by the offline benchmark), --no_share_hessians.
 """
 from __future__ import annotations
@@ -69,6 +69,9 @@ def parse_args(argv=None):
     p.add_argument("--random_init_config", type=str, default=None,
                    help="JSON file with LlamaConfig kwargs: build a random-init model instead of loading weights")
     p.add_argument("--no_share_hessians", action="store_true")
+    p.add_argument("--mode", type=str, default="exact", choices=["exact", "fast"],
+                   help="exact: the reference's fp32 rank-k arithmetic, bit-identical bytes given (W, U); fast: rank-k updates on "
+                        "tcgen05 tensor cores (fp32-class accuracy, ~2x faster column loops)")
     p.add_argument("--rtn_fp32_arith", action="store_true",
                    help="embed_tokens / lm_head of a 16-bit model: widen the weights to fp32 for the scale search instead of "
                         "searching in the weight's own arithmetic like the reference does")
@@ -148,7 +151,7 @@ def main(argv=None):
         model, data_loader=calibration_data, quantizable_modules=args.quantizable_modules,
         quantizer_kwargs=dict(rel_damp=args.rel_damp, block_size=args.block_size, act_order=args.act_order,
                               quant_scale=args.quant_scale, static_groups=args.static_groups, rmin=args.rmin,
-                              rdelta=args.rdelta, nstep=args.nstep, verbose=args.verbose),
+                              rdelta=args.rdelta, nstep=args.nstep, verbose=args.verbose, mode=args.mode),
         pre_block_modules=args.pre_block_modules, block_modules=args.block_modules,
         post_block_modules=args.post_block_modules, quant_non_block_modules=args.quant_non_block_modules,
         cpu_offload_modules=args.cpu_offload_modules, cpu_offload_activations=args.cpu_offload_activations,

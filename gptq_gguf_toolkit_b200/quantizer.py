@@ -44,6 +44,9 @@ def _world() -> int:
     return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
 
 
+_BCAST_GROUPS: dict = {}      # (chain slot, world size) -> process group, see Quantizer._bcast_group
+
+
 class PhaseTimer:
     """CUDA-event phase timing without synchronising inside the run; totals() syncs once at the end."""
 
@@ -149,7 +152,6 @@ class Quantizer:
         # several ranks: every Cholesky chain (gq_prepare) of a block runs on ONE owner rank and U is broadcast, instead of
         # every rank running all of them (the reference factors on every rank too, gptq.py:305-324 is not rank-guarded)
         self.shard_prepare = shard_prepare
-        self._bcast_groups: dict = {}
         self.fused_installed: List[str] = []
         self._split_ok: Optional[bool] = None
         self._side_streams: list = []
@@ -321,9 +323,10 @@ class Quantizer:
         """One process group (NCCL communicator) per chain slot: a broadcast of U waits for its chain on the side stream,
         and collectives of one communicator execute in issue order -- on the default group the short chains' results and
         the all-gathers would queue behind the longest chain."""
-        if gi not in self._bcast_groups:
-            self._bcast_groups[gi] = dist.new_group(ranks=list(range(_world())))
-        return self._bcast_groups[gi]
+        key = (gi, _world())      # process-wide: creating a communicator costs ~0.5 s, a Quantizer may be created per run
+        if key not in _BCAST_GROUPS:
+            _BCAST_GROUPS[key] = dist.new_group(ranks=list(range(_world())))
+        return _BCAST_GROUPS[key]
 
     def _prepare_or_receive(self, gi: int, handles, H, W, rel_damp, side, slot):
         """gq_prepare on the chain's owner rank + broadcast of (U, not-PD flag) on the chain's stream; plain ops.prepare with

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #endif
 
+#define CD4_PROFILE 1
 #include "../../gptq_gguf_toolkit_b200/csrc/chol_diag_v4.cuh"
 using namespace cd4;
 
@@ -83,6 +84,19 @@ int main() {
     CK(cudaEventElapsedTime(&ms, e0, e1));
     printf("%s   chol_diag_v4: %.1f us per launch (v3 70.4 us, v2 88.7 us, v1 129 us on B200)\n", ok ? "OK" : "MISMATCH",
            1e3 * ms / reps);
+    {
+        unsigned long long z[8] = {0}, c[8];
+        CK(cudaMemcpyToSymbol(cd4_clk, z, sizeof(z)));
+        chol_diag_v4_kernel<<<1, T4, sizeof(Smem4)>>>(dA, dB, dBT, n, k0, dflag);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpyFromSymbol(c, cd4_clk, sizeof(c)));
+        const char *nm[7] = {"load", "warp-factor x4", "panel-solve x3", "trailing x3", "diag-inverse", "offdiag-inverse", "store"};
+        unsigned long long tot = 0;
+        for (int i = 0; i < 7; ++i) tot += c[i];
+        printf("phase cycles (thread 0, one launch, total %llu):", tot);
+        for (int i = 0; i < 7; ++i) printf("  %s %llu", nm[i], c[i]);
+        printf("\n");
+    }
     return ok ? 0 : 2;
 }
 #endif  // SIMT_EMU

@@ -30,6 +30,12 @@ if "prepare" in what:
     x = torch.randn(2 * n, n, device="cuda")
     H = (x.T @ x) / n
     ops.prepare(H, torch.randn(256, n, device="cuda"), 0.01)
+if "prepare_big" in what:      # one Cholesky chain at down_proj's width (813 launches)
+    nb = 14336
+    x = torch.randn(nb // 2, nb, device="cuda")
+    H = (x.T @ x) / nb + 0.5 * torch.eye(nb, device="cuda")
+    del x
+    ops.prepare(H, torch.randn(256, nb, device="cuda"), 0.01)
 if "hessian" in what:
     X = torch.randn(16384, n, device="cuda").to(torch.bfloat16)
     H = torch.zeros(n, n, device="cuda")

@@ -101,3 +101,25 @@ def test_gemm_wide_dynamic_range_inside_rows(gemm):
     # 4.0e-6 for 3xTF32, below 2e-6 for the fp16 pair)
     err = (Cm.double() - A.double() @ B.double().T).abs().max().item()
     assert err <= 5e-6 * (A.double().abs() @ B.double().abs().T).max().item()
+
+
+def test_f16x3_b_is_row_prefix_of_a():
+    """gemm_f16x3_nt with same_ab and N < M: B = the first N rows of A, split once (the left-looking update of the grouped
+    Cholesky in csrc/linalg.cu); the debug hook sets same_ab only for M == N, so this goes through gq_prepare's own check:
+    a grouped factorisation (GQ_PREPARE_GROUP=4) must agree with the ungrouped one to fp32 accuracy."""
+    import os
+    from gptq_gguf_toolkit_b200 import ops
+    torch.manual_seed(3)
+    n = 1536
+    x = torch.randn(2 * n, n, device="cuda")
+    H = (x.T @ x) / n
+    W = torch.randn(64, n, device="cuda")
+    res = {}
+    for grp in ("1", "4"):
+        os.environ["GQ_PREPARE_GROUP"] = grp
+        U, flag = ops.prepare(H.clone(), W, 0.01)
+        torch.cuda.synchronize()
+        assert int(flag.item()) == 0
+        res[grp] = U
+    os.environ.pop("GQ_PREPARE_GROUP", None)
+    assert float((res["1"] - res["4"]).abs().max() / res["1"].abs().max()) <= 2e-5
