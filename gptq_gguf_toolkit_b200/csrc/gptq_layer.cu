@@ -250,6 +250,10 @@ extern "C" size_t gq_gptq_workspace_bytes(int d_row, int d_col, int mode) {
 int gq_search_all_superblocks(const float *W, int d_row, int d_col, int qtype, double rmin, double rdelta, int nstep,
                               uint16_t *d, uint16_t *dmin, void *sq, void *zq, uint32_t *search_flags, cudaStream_t st);
 
+int gq_gptq_blocksize(float *W, const float *U, int d_row, int d_col, int qtype, int B, double rmin, double rdelta, int nstep,
+                      bool searched, void *qweight, uint16_t *d, void *sq, uint16_t *dmin, void *zq, uint8_t *packed, void *wdeq,
+                      int wdeq_dtype, uint32_t *flags, cudaStream_t st);
+
 extern "C" int gq_gptq_quantize_ex(float *W, const float *U, int d_row, int d_col, int qtype, int block_size,
                                    double rmin, double rdelta, int nstep, int mode, int static_groups, const int *perm,
                                    void *qweight, uint16_t *d, void *sq, uint16_t *dmin, void *zq, uint8_t *packed, void *wdeq,
@@ -262,8 +266,8 @@ extern "C" int gq_gptq_quantize_ex(float *W, const float *U, int d_row, int d_co
     GQ_REQUIRE(((uintptr_t)W | (uintptr_t)U | (uintptr_t)qweight) % 16 == 0, "gq_gptq_quantize: W, U, qweight must be 16-byte aligned");
     GQ_REQUIRE(wdeq == nullptr || ((uintptr_t)wdeq % 16 == 0 && wdeq_dtype >= GQ_F32 && wdeq_dtype <= GQ_BF16),
                "gq_gptq_quantize: bad wdeq");
-    if (block_size != 128) {
-        gq_set_error("gq_gptq_quantize: block_size=%d not implemented (only 128, the run_quant.sh default)", block_size);
+    if (block_size != 128 && block_size != 32 && block_size != 64 && block_size != 256) {
+        gq_set_error("gq_gptq_quantize: block_size=%d not implemented (32, 64, 128 and 256 are; run_quant.sh uses 128)", block_size);
         return GQ_ERR_UNSUPPORTED;
     }
     GQ_REQUIRE(mode >= GQ_MODE_EXACT && mode <= GQ_MODE_EXACT_RIGHT, "gq_gptq_quantize: unknown mode %d", mode);
@@ -278,6 +282,18 @@ extern "C" int gq_gptq_quantize_ex(float *W, const float *U, int d_row, int d_co
         return GQ_ERR_UNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (block_size != 128) {      // the other block sizes of the reference: plain right-looking schedule (gptq_blocksize.cu)
+        if (mode == GQ_MODE_FAST || perm != nullptr || static_groups == 2) {
+            gq_set_error("gq_gptq_quantize: block_size=%d is implemented for the exact arithmetic without act_order only", block_size);
+            return GQ_ERR_UNSUPPORTED;
+        }
+        if (static_groups == 1) {
+            const int rc = gq_search_all_superblocks(W, d_row, d_col, qtype, rmin, rdelta, nstep, d, dmin, sq, zq, search_flags, st);
+            if (rc) return rc;
+        }
+        return gq_gptq_blocksize(W, U, d_row, d_col, qtype, block_size, rmin, rdelta, nstep, static_groups == 1, qweight, d, sq, dmin,
+                                 zq, packed, wdeq, wdeq_dtype, search_flags, st);
+    }
     if (static_groups == 1) {     // gptq.py:184-196: all scales / zeros up front, on the weights as they are now
         const int rc = gq_search_all_superblocks(W, d_row, d_col, qtype, rmin, rdelta, nstep, d, dmin, sq, zq, search_flags, st);
         if (rc) return rc;

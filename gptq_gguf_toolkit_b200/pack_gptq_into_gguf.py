@@ -19,7 +19,9 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
+from hashlib import sha256
 from typing import Dict, Iterable, Optional, Tuple
 
 import numpy as np
@@ -65,6 +67,63 @@ def _iter_state(model_or_state) -> Iterable[Tuple[str, torch.Tensor]]:
         yield name, t
 
 
+# llama.cpp identifies a BPE pre-tokenizer by hashing the token ids of a fixed probe text (the reference's vendored converter,
+# get_vocab_base_pre, quant/gptq/pack_gptq_into_gguf.py:721-949, carries ~100 such hashes).  The probe text and the hashes are
+# DATA that must match llama.cpp's; this writer knows the Llama-family ones and refuses the rest (use the reference converter).
+_PRE_PROBE = ('\n \n\n \n\n\n \t \t\t \t\n  \n   \n    \n     \n🚀 (normal) 😶\u200d🌫\ufe0f (multiple emojis concatenated) '
+              '\u2705 🦙🦙 3 33 333 3333 33333 333333 3333333 33333333 3.3 3..3 3...3 '
+              '\u1780\u17b6\u1793\u17cb\u178f\u17c2\u1796\u17b7\u179f\u17c1\u179f\u17a2\u17b6\u1785😁 ?\u6211\u60f3\u5728apple\u5de5\u4f5c1314151\u5929\uff5e '
+              '------======= \u043d\u0435\u0449\u043e \u043d\u0430 \u0411\u044a\u043b\u0433\u0430\u0440\u0441\u043a\u0438 \'\'\'\'\'\'```````""""......!!!!!!?????? '
+              'I\'ve been \'told he\'s there, \'RE you sure? \'M not sure I\'ll make it, \'D you like some tea? We\'Ve a\'lL')
+_PRE_HASHES = {
+    "0ef9807a4087ebef797fc749390439009c3b9eda9ad1a097abbe738f486c01e5": "llama-bpe",      # Meta-Llama-3 / 3.1 / 3.2
+    "b6e8e1518dc4305be2fe39c313ed643381c4da5db34a98f6a04c093f8afbe99b": "qwen2",
+}
+
+
+def bpe_pre_tokenizer(hf_dir: str) -> str:
+    """tokenizer.ggml.pre of a BPE model (reference set_vocab -> get_vocab_base_pre -> add_tokenizer_pre, :682, 957)."""
+    from transformers import AutoTokenizer
+    tok = AutoTokenizer.from_pretrained(hf_dir)
+    h = sha256(str(tok.encode(_PRE_PROBE)).encode()).hexdigest()
+    if h not in _PRE_HASHES:
+        raise NotImplementedError(f"BPE pre-tokenizer with probe hash {h} is not known to this writer; convert with the reference's "
+                                  "quant/gptq/pack_gptq_into_gguf.py (it reads the same data.pth files)")
+    return _PRE_HASHES[h]
+
+
+def llama3_rope_factors(cfg: dict, rope_scaling: dict) -> torch.Tensor:
+    """rope_freqs.weight of a Llama-3.1-style model (rope_type "llama3"): per frequency 1, `factor`, or the smooth blend
+    between them, by wavelength against original_max_position_embeddings / {high, low}_freq_factor (the published Llama 3.1
+    scaling rule; reference LlamaModel.generate_extra_tensors, :2259-2287)."""
+    base = float(cfg.get("rope_theta") or rope_scaling.get("rope_theta") or 10000.0)
+    dim = cfg.get("head_dim") or cfg["hidden_size"] // cfg["num_attention_heads"]
+    freqs = 1.0 / (base ** (torch.arange(0, dim, 2, dtype=torch.float32) / dim))
+    factor = rope_scaling.get("factor", 8.0)
+    lo_f, hi_f = rope_scaling.get("low_freq_factor", 1.0), rope_scaling.get("high_freq_factor", 4.0)
+    old_ctx = rope_scaling.get("original_max_position_embeddings") or cfg.get("original_max_position_embeddings", 8192)
+    out = []
+    for f in freqs:
+        wavelen = 2 * math.pi / f
+        if wavelen < old_ctx / hi_f:
+            out.append(1.0)
+        elif wavelen > old_ctx / lo_f:
+            out.append(float(factor))
+        else:
+            smooth = (old_ctx / wavelen - lo_f) / (hi_f - lo_f)
+            out.append(float(1 / ((1 - smooth) / factor + smooth)))
+    return torch.tensor(out, dtype=torch.float32)
+
+
+def _rope_scaling(cfg: dict) -> dict:
+    rs = cfg.get("rope_scaling") or {}
+    if not rs:      # transformers >= 5 keeps it under rope_parameters
+        rp = cfg.get("rope_parameters") or {}
+        if rp.get("rope_type", "default") not in ("default", None):
+            rs = rp
+    return rs
+
+
 def _add_vocab(writer: gguf.GGUFWriter, hf_dir: Optional[str], vocab_size: int) -> str:
     """Tokenizer metadata.  With a real HF directory the upstream vocab loaders are used; without one (random-init
     benchmark models, no network) a placeholder vocabulary of the right size keeps the file loadable."""
@@ -79,12 +138,16 @@ def _add_vocab(writer: gguf.GGUFWriter, hf_dir: Optional[str], vocab_size: int) 
                 while len(toks) < vocab_size:
                     toks.append(f"[PAD{len(toks)}]".encode()); scores.append(-1000.0); types.append(int(gguf.TokenType.UNUSED))
                 writer.add_tokenizer_model("gpt2" if cls is gguf.BpeVocab else "llama")
+                if cls is gguf.BpeVocab:
+                    writer.add_tokenizer_pre(bpe_pre_tokenizer(hf_dir))
                 writer.add_token_list(toks)
                 if cls is not gguf.BpeVocab:
                     writer.add_token_scores(scores)
                 writer.add_token_types(types)
                 gguf.SpecialVocab(Path(hf_dir), load_merges=cls is gguf.BpeVocab, n_vocab=len(toks)).add_to_gguf(writer)
                 return cls.__name__
+            except NotImplementedError:
+                raise
             except Exception:      # noqa: BLE001 -- try the next loader, as the reference's set_vocab does (:2120-2136)
                 continue
     writer.add_tokenizer_model("llama")
@@ -121,12 +184,31 @@ def write_gguf(model_or_state, config, dir_model_quant: str, outfile: str, outty
     if rope_theta is not None:
         w.add_rope_freq_base(float(rope_theta))
     w.add_layer_norm_rms_eps(float(cfg.get("rms_norm_eps", 1e-5)))
+    # RoPE scaling (reference LlamaModel.set_gguf_parameters :2172-2175, 2306-2310; generate_extra_tensors :2259-2287)
+    rs = _rope_scaling(cfg)
+    rs_type = str(rs.get("rope_type", rs.get("type", ""))).lower() if rs else ""
+    rope_freqs = None
+    if rs_type == "linear" and "factor" in rs:
+        w.add_rope_scaling_type(gguf.RopeScalingType.LINEAR)
+        w.add_rope_scaling_factor(rs["factor"])
+    elif rs_type == "yarn" and "factor" in rs:
+        w.add_rope_scaling_type(gguf.RopeScalingType.YARN)
+        w.add_rope_scaling_factor(rs["factor"])
+        w.add_rope_scaling_orig_ctx_len(rs["original_max_position_embeddings"])
+    elif rs_type == "llama3":
+        rope_freqs = llama3_rope_factors(cfg, rs)
+    elif rs_type not in ("", "default"):
+        raise NotImplementedError(f"rope_scaling type {rs_type!r}: use the reference's vendored converter")
     vocab_kind = _add_vocab(w, hf_dir, cfg["vocab_size"])
     w.add_description(f"GPTQ K-quant tensors from {os.path.abspath(dir_model_quant)}; vocab: {vocab_kind}")
 
     tmap = gguf.get_tensor_name_map(gguf.MODEL_ARCH.LLAMA, n_layer)
     written: Dict[str, str] = {}
     n_k = 0
+    if rope_freqs is not None:
+        rname = gguf.TENSOR_NAMES[gguf.MODEL_TENSOR.ROPE_FREQS] + ".weight"
+        w.add_tensor(rname, rope_freqs.numpy(), raw_dtype=gguf.GGMLQuantizationType.F32)
+        written[rname] = "F32"
     tied = bool(cfg.get("tie_word_embeddings", False))
     for hf_name, t in _iter_state(model_or_state):
         if tied and hf_name == "lm_head.weight":

@@ -113,7 +113,8 @@ GQ_API int gq_prepare(float *H, const float *W, int d_row, int d_col, float rel_
  *          candidate for the whole call when no group is valid (quant_utils.py:250-252); this library
  *          never skips, so (flags[2s+1] & ~flags[2s]) != 0 marks the (degenerate) inputs on which the
  *          two can differ.  Must be zero-initialised by the caller.
- * block_size must be 128 (the reference's run_quant.sh default).
+ * block_size: 128 (the reference's run_quant.sh default: the fused kernels) or 32 / 64 / 256 (a plain right-looking schedule with
+ * the same arithmetic, exact modes only, no act_order); other values return GQ_ERR_UNSUPPORTED.
  * mode GQ_MODE_FAST needs gq_gptq_workspace_bytes() of scratch (the exact modes need none): the rank-k updates between
  * 256-column super-blocks then run as tcgen05 split-fp16 GEMMs (fp32-class accuracy, NOT bit-identical to the reference).
  * GQ_MODE_EXACT / _LEFT / _RIGHT give bit-identical outputs (see gq_mode); they differ in the number of launches. */

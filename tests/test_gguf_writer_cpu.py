@@ -69,3 +69,38 @@ def test_reference_schema_without_packed_needs_cuda(monkeypatch, tmp_path):
         pytest.skip("CUDA present: the GPU packer handles this case")
     with pytest.raises((GQError, RuntimeError, AssertionError)):
         write_gguf(model, model.config, save_dir, str(tmp_path / "x.gguf"))
+
+
+def test_llama3_rope_scaling_and_unknown_types(monkeypatch, tmp_path):
+    """rope_scaling of type llama3 (Llama 3.1 / 3.2) must produce rope_freqs.weight like the reference's generate_extra_tensors
+    (pack_gptq_into_gguf.py:2259-2287); linear scaling the two KVs (:2172-2175); unknown types are refused."""
+    from gptq_gguf_toolkit_b200.pack_gptq_into_gguf import llama3_rope_factors, write_gguf
+    model, q, save_dir = _run_driver(monkeypatch, tmp_path, "w")
+    cfg = model.config.to_dict()
+    cfg.pop("rope_parameters", None)
+    cfg["rope_theta"] = 500000.0
+    cfg["rope_scaling"] = {"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+                           "original_max_position_embeddings": 64}
+    out = str(tmp_path / "l3.gguf")
+    written = write_gguf(model, cfg, save_dir, out)
+    assert written["rope_freqs.weight"] == "F32"
+    reader, tensors = _read(out)
+    f = np.asarray(tensors["rope_freqs.weight"].data)
+    want = llama3_rope_factors(cfg, cfg["rope_scaling"]).numpy()
+    assert f.shape == (cfg["hidden_size"] // cfg["num_attention_heads"] // 2,) and np.array_equal(f, want)
+    assert f[0] == 1.0 and f[-1] == 8.0 and np.all(np.diff(f) >= 0)          # high frequencies untouched, low ones stretched
+    # the published rule, restated independently for one mid-band frequency
+    dim, base = cfg["hidden_size"] // cfg["num_attention_heads"], 500000.0
+    mid = [i for i in range(dim // 2) if 1.0 < f[i] < 8.0]
+    for i in mid[:2]:
+        wl = 2 * np.pi * base ** (2 * i / dim)
+        smooth = (64 / wl - 1.0) / (4.0 - 1.0)
+        assert abs(f[i] - 1 / ((1 - smooth) / 8.0 + smooth)) < 1e-5
+    cfg["rope_scaling"] = {"rope_type": "linear", "factor": 2.0}
+    write_gguf(model, cfg, save_dir, str(tmp_path / "lin.gguf"))
+    r2, _ = _read(str(tmp_path / "lin.gguf"))
+    kv = {x.name: x for x in r2.fields.values()}
+    assert float(kv["llama.rope.scaling.factor"].parts[-1][0]) == 2.0
+    cfg["rope_scaling"] = {"rope_type": "longrope", "factor": 2.0}
+    with pytest.raises(NotImplementedError):
+        write_gguf(model, cfg, save_dir, str(tmp_path / "bad.gguf"))

@@ -96,13 +96,41 @@ def test_step_rejects_unsupported(ops):
     W = torch.zeros(32, 256, device="cuda")
     U = torch.eye(256, device="cuda")
     with pytest.raises(GQError) as e:
-        ops.gptq_quantize(W, U, 12, block_size=64)
+        ops.gptq_quantize(W, U, 12, block_size=96)          # 32 / 64 / 128 / 256 are implemented
+    assert e.value.status == GQ_ERR_UNSUPPORTED
+    with pytest.raises(GQError) as e:
+        ops.gptq_quantize(W, U, 12, block_size=64, mode=1)  # the other block sizes: exact arithmetic only
     assert e.value.status == GQ_ERR_UNSUPPORTED
     with pytest.raises(GQError) as e:
         ops.gptq_quantize(W, U, 99)
     assert e.value.status == GQ_ERR_INVALID
     with pytest.raises(GQError):
         ops.gptq_quantize(torch.zeros(32, 256), torch.eye(256), 12)     # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("bs", [32, 64, 256])
+@pytest.mark.parametrize("tname", list(TYPES))
+def test_step_other_block_sizes_golden(ops, golden_dir, tname, bs):
+    """--block_size 32 / 64 / 256 (gptq.py:55, 219-270): csrc/gptq_blocksize.cu against the reference's own outputs
+    (tests/golden/blocksize_a.npz, make_golden_blocksize.py): five tensors, GGUF bytes and dequantised weights, bit for bit;
+    and against the oracle on a wider, ragged problem."""
+    g = np.load(os.path.join(golden_dir, "blocksize_a.npz"))
+    W, U = dev(g["W"]), dev(np.ascontiguousarray(g["U_colmajor_T"].T))
+    out = ops.gptq_quantize(W, U, TYPES[tname], block_size=bs, wdeq_dtype=torch.float32)
+    torch.cuda.synchronize()
+    want = [g[f"bs{bs}_{tname}_{k}"] for k in ("qweight", "d", "sq", "dmin", "zq")]
+    for got, w, k in zip(out[:5], want, KEYS):
+        assert np.array_equal(raw(got), w), f"bs{bs}/{tname}: {k}"
+    assert np.array_equal(out[5].cpu().numpy(), g[f"bs{bs}_{tname}_packed"])
+    assert np.array_equal(out[6].cpu().numpy(), g[f"bs{bs}_{tname}_dequant"])
+    rng = np.random.default_rng(bs)
+    Wn = (rng.standard_normal((45, 1280)) * 0.05).astype(np.float32)
+    Un = (np.triu(rng.standard_normal((1280, 1280)) * 0.01) + np.eye(1280)).astype(np.float32)
+    ref = orc.gptq_step(Wn, Un, TYPES[tname], bs)
+    out = ops.gptq_quantize(dev(Wn), dev(Un), TYPES[tname], block_size=bs, wdeq_dtype=torch.bfloat16, static_groups=False)
+    torch.cuda.synchronize()
+    assert_five_equal(out[:5], ref[:5], f"bs{bs}/{tname} vs oracle")
+    assert torch.equal(out[6].cpu(), torch.from_numpy(ref[5]).to(torch.bfloat16))
 
 
 def test_step_all_zero_weights(ops):

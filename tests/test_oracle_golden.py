@@ -162,3 +162,17 @@ def test_rtn_fp16_arithmetic_matches_reference_golden(golden_dir, tname):
     for k, a in zip(("qweight", "d", "sq", "dmin", "zq"), out):
         a = a.view(np.uint16) if a.dtype == np.float16 else a
         assert np.array_equal(a.view(np.uint8), g[f"{tname}_{k}"].view(np.uint8)), f"{tname}.{k}"
+
+
+@pytest.mark.parametrize("bs", [32, 64, 256])
+@pytest.mark.parametrize("tname", list(TYPES))
+def test_step_other_block_sizes_match_reference(golden_dir, tname, bs):
+    """GPTQ.step with --block_size 32 / 64 / 256 (gptq.py:55, 219-270): the oracle against the reference's own outputs
+    (tests/golden/blocksize_a.npz, generated by make_golden_blocksize.py), bit for bit."""
+    g = _load(golden_dir, "blocksize_a.npz")
+    o = orc.gptq_step(g["W"], _U(g), TYPES[tname], block_size=bs)
+    got = _five_raw(o)
+    for k in KEYS:
+        assert np.array_equal(got[k], g[f"bs{bs}_{tname}_{k}"]), f"bs{bs} {tname} {k}"
+    assert np.array_equal(o[5], g[f"bs{bs}_{tname}_dequant"])
+    assert np.array_equal(orc.pack(TYPES[tname], *o[:5]), g[f"bs{bs}_{tname}_packed"])
