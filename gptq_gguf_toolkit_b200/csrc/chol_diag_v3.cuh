@@ -1,7 +1,6 @@
-// chol_diag_v3.cuh -- EXPERIMENTAL register-resident variant of the (128 x 128) diagonal-block kernel of gq_prepare
-// (csrc/linalg.cu: chol_diag_v2_kernel, 88.7 us on B200, issue-bound).  Selected by GQ_DIAG_V2=3; NOT yet run on hardware
-// (written after round 1's GPU budget was spent) -- verified for indexing / algorithm on the SIMT emulator of the CPU suite
-// (tests/test_simt_emu_cpu.py) and timed by profiles/microbench/chol_diag_v3.cu.
+// chol_diag_v3.cuh -- register-resident variant (GQ_DIAG_V2=3; superseded as the default by chol_diag_v4.cuh) of the (128 x 128) diagonal-block kernel of gq_prepare
+// (csrc/linalg.cu: chol_diag_v2_kernel, 88.7 us on B200, issue-bound): 70.4 us on B200 (round 2), meets the same accuracy bounds
+// (tests/test_gpu_parity.py); also run on the SIMT emulator of the CPU suite (tests/test_simt_emu_cpu.py).
 // Same contract as chol_diag_v2_kernel: factor A[k0:k0+128, k0:k0+128] = L L^T in place (lower), inv(L) to Binv, inv(L)^T to
 // BinvT (may be null).
 //   * inside a 32-column panel every thread keeps ITS 16 panel entries of one row in registers (256 threads = 128 rows x 2

@@ -1,4 +1,4 @@
-// kquant_bf16.cuh -- the K-quant scale search in the reference's BF16 (or FP16) arithmetic (EXPERIMENTAL: written at the end of round 1
+// kquant_bf16.cuh -- the K-quant scale search in the reference's BF16 (or FP16) arithmetic (written at the end of round 1, validated on B200 in round 2:
 // after the GPU budget was spent; the CPU restatement of the same arithmetic that the tests check against is pinned bit for
 // bit to the reference -- tests/golden/rtn_bf16.npz -- and is what this code has to match on the first GPU run of round 2).
 //

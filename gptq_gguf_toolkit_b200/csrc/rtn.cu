@@ -29,7 +29,7 @@ template <int QT> int launch_rtn(const RtnParams &p, cudaStream_t st) {
     return GQ_OK;
 }
 
-// EXPERIMENTAL twin of rtn_kernel for BF16 / FP16 weights with the reference's scale search in that dtype's arithmetic; the
+// Twin of rtn_kernel for BF16 / FP16 weights with the reference's scale search in that dtype's arithmetic; the
 // body lives in rtn_native.cuh.  Reached only through gq_rtn_quantize_native; gq_rtn_quantize is untouched.
 template <int QT, int RND>
 __global__ void __launch_bounds__(NT) rtn_bf16_kernel(const RtnParams p) {
@@ -125,7 +125,7 @@ extern "C" int gq_rtn_quantize(const void *W, int w_dtype, int d_row, int d_col,
     return dispatch_rtn(qtype, p, (cudaStream_t)stream);
 }
 
-// EXPERIMENTAL (see kquant_bf16.cuh): gq_rtn_quantize for a BF16 / FP16 weight with the scale search in the weight's own
+// (see kquant_bf16.cuh) gq_rtn_quantize for a BF16 / FP16 weight with the scale search in the weight's own
 // arithmetic -- what quantizer.py:278-330 computes for embed_tokens / lm_head of a 16-bit model.  Same outputs and conventions.
 extern "C" int gq_rtn_quantize_native(const void *W, int w_dtype, int d_row, int d_col, int qtype, double rmin,
                                       double rdelta, int nstep, void *qweight, uint16_t *d, void *sq, uint16_t *dmin,

@@ -1,4 +1,4 @@
-// rtn_native.cuh -- bodies of the RTN kernels of csrc/rtn.cu -- the shipped rtn_kernel (fp32 arithmetic) and the EXPERIMENTAL
+// rtn_native.cuh -- bodies of the RTN kernels of csrc/rtn.cu -- the shipped rtn_kernel (fp32 arithmetic) and its
 // native-arithmetic twin (gq_rtn_quantize_native) -- in a header of their own so that the CPU suite can run them on the SIMT
 // emulator (tests/test_simt_emu_cpu.py).
 // Params / Smem are rtn.cu's RtnParams / RtnSmem (template parameters here only because those live in rtn.cu).
@@ -6,7 +6,7 @@
 #include "tile.cuh"
 #include "kquant_bf16.cuh"
 
-// EXPERIMENTAL twin of rtn_kernel for BF16 / FP16 weights with the reference's scale search in that dtype's arithmetic (kquant_bf16.cuh);
+// Twin of rtn_kernel for BF16 / FP16 weights with the reference's scale search in that dtype's arithmetic (kquant_bf16.cuh);
 // everything after the search -- quantize() in fp32, codes, GGUF bytes, dequantised weights -- is the same code.
 // Reached only through gq_rtn_quantize_native; gq_rtn_quantize (fp32 search on widened weights) is untouched.
 template <int QT, int RND, int R, int NT, class Params, class Smem>

@@ -193,8 +193,8 @@ def rtn_quantize(W: torch.Tensor, q_type: int, rmin: float = -1.0, rdelta: float
                  packed: bool = True, wdeq_dtype: Optional[torch.dtype] = None, native_arith: bool = False):
     """RTN K-quant of a weight without Hessian (quantizer.py:278-330).  W is read-only (fp32/fp16/bf16).
     Returns (qweight, d, sq, dmin, zq, packed|None, wdeq|None).
-    native_arith (EXPERIMENTAL, see gq_rtn_quantize_native): for a bf16 weight run the scale search in bf16 arithmetic like
-    the reference does; default False = widen to fp32 (the validated path)."""
+    native_arith (gq_rtn_quantize_native): for a bf16 / fp16 weight run the scale search in that dtype's arithmetic like the
+    reference does (quantizer.py:303-305) -- what the driver passes for embed_tokens / lm_head; False = widen to fp32."""
     L.require_cuda(W)
     assert W.is_contiguous() and W.dim() == 2
     d_row, d_col = W.shape

@@ -613,36 +613,65 @@ class Quantizer:
         return fronts
 
     # -------------------------------------------------------------------------------------------
+    @staticmethod
+    def _same_kwargs(k0, k) -> bool:
+        if k.keys() != k0.keys():
+            return False
+        for key, v in k.items():
+            v0 = k0[key]
+            if isinstance(v, torch.Tensor):
+                if not (isinstance(v0, torch.Tensor) and v.shape == v0.shape and torch.equal(v, v0)):
+                    return False
+            elif isinstance(v, (tuple, list)) and all(isinstance(t, torch.Tensor) for t in v):
+                if not (isinstance(v0, (tuple, list)) and len(v0) == len(v) and
+                        all(a.shape == b.shape and torch.equal(a, b) for a, b in zip(v, v0))):
+                    return False
+            elif v is not v0 and v != v0:
+                return False
+        return True
+
     def _batched_inputs(self, input_args, input_kwargs):
-        """Merge per-sequence captures into batches when they only differ in hidden_states."""
+        """Merge per-sequence captures into batches: RUNS of consecutive sequences that only differ in hidden_states (same
+        shape, equal keyword arguments) become one batch of up to `calibration_batch_size` sequences; anything else stays a
+        batch of its own (fineweb_edu keeps the short tails of its documents, data_utils.py, so lengths may differ)."""
         bs = self.calibration_batch_size
         n = len(input_args)
-        ok = bs > 1 and n > 1 and all(len(a) == 1 and isinstance(a[0], torch.Tensor) for a in input_args)
-        if ok:
-            shp = input_args[0][0].shape
-            ok = all(a[0].shape == shp and a[0].shape[0] == 1 for a in input_args)
-        if ok:
-            k0 = input_kwargs[0]
-            for k in input_kwargs[1:]:
-                if k.keys() != k0.keys():
-                    ok = False
-                    break
-                for key, v in k.items():
-                    v0 = k0[key]
-                    if isinstance(v, torch.Tensor):
-                        if not (isinstance(v0, torch.Tensor) and v.shape == v0.shape and torch.equal(v, v0)):
-                            ok = False
-                    elif isinstance(v, (tuple, list)) and all(isinstance(t, torch.Tensor) for t in v):
-                        if not all(torch.equal(a, b) for a, b in zip(v, v0)):
-                            ok = False
-                    elif v is not v0 and v != v0:
-                        ok = False
-                if not ok:
-                    break
-        if not ok:
+        simple = bs > 1 and n > 1 and all(len(a) == 1 and isinstance(a[0], torch.Tensor) and a[0].shape[0] == 1 for a in input_args)
+        if not simple:
             return [(list(a), k) for a, k in zip(input_args, input_kwargs)]
-        hs = torch.cat([a[0] for a in input_args], dim=0)
-        return [([hs[i:i + bs]], input_kwargs[0]) for i in range(0, n, bs)]
+        out, i = [], 0
+        while i < n:
+            j = i + 1
+            while (j < n and j - i < bs and input_args[j][0].shape == input_args[i][0].shape
+                   and input_args[j][0].device == input_args[i][0].device and self._same_kwargs(input_kwargs[i], input_kwargs[j])):
+                j += 1
+            if j - i == 1:
+                out.append((list(input_args[i]), input_kwargs[i]))
+            else:
+                out.append(([torch.cat([a[0] for a in input_args[i:j]], dim=0)], input_kwargs[i]))
+            i = j
+        return out
+
+    def _front_capacity(self, tail, batches, device) -> int:
+        """How many batches' (residual, last-layer input) pairs the deferred tail of pass 2 may keep on the GPU: they cost
+        tokens x (hidden + in_features of the last layer) elements -- 120 GB for Llama-3-8B at 4M calibration tokens -- so the
+        split is limited to half of the memory that is free right now; the remaining batches take the plain path after the
+        deferred layer has finished."""
+        try:
+            free, _ = torch.cuda.mem_get_info(device)
+        except Exception:  # noqa: BLE001
+            return len(batches)
+        budget = free // 2
+        d_in = getattr(tail["last"], "in_features", 0)
+        used, k = 0, 0
+        for a, _ in batches:
+            x = a[0]
+            need = (x.numel() // x.shape[-1]) * (x.shape[-1] + d_in) * x.element_size()
+            if used + need > budget:
+                break
+            used += need
+            k += 1
+        return k
 
     # -------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -744,13 +773,17 @@ class Quantizer:
                 # batches while that layer's Cholesky chain and column loop are still in flight on a side stream
                 # (the block forwards are streams of short kernels, so the latency-bound chain interleaves with
                 # them instead of idling the GPU); then the layer itself + the residual add for all batches.
-                fronts = self._split_fronts(block, tail, batches, device)
+                k_front = self._front_capacity(tail, batches, device)
+                fronts = self._split_fronts(block, tail, batches[:k_front], device)
                 finish()
                 with self.timer.span("forward2"):
-                    for (inp_args, _), (res, din) in zip(batches, fronts):
+                    for (inp_args, _), (res, din) in zip(batches[:k_front], fronts):
                         out = res + tail["last"](din)
                         inp_args[0].copy_(out)
-                del fronts
+                    del fronts
+                    for inp_args, inp_kwargs in batches[k_front:]:      # did not fit the memory budget: plain forward
+                        out = maybe_first_element(block(*to(inp_args, device=device), **to(inp_kwargs, device=device)))
+                        inp_args[0].copy_(out)
             if self.cpu_offload_modules:
                 block = block.cpu()
             del handles, hooks
@@ -768,13 +801,22 @@ class Quantizer:
             with self.timer.span("save_wait"):
                 self._saver.close()
             self._saver = None
-        for names, flag in self._mask_flags:      # deferred check (a device flag per shared-input group)
-            if bool(flag.item()):
-                raise RuntimeError(f"layers {names} share an input but have different all-zero weight columns; "
-                                   "rerun with share_hessians=False")
+        # Deferred validity check of the shared-Hessian groups (one device flag per group, no host sync inside the run): members
+        # of a group must have the SAME all-zero weight columns, otherwise the shared U is wrong for some of them
+        # (gptq.py:308-313 builds U per layer).  Every rank evaluates the same flags (W is replicated), the verdict is
+        # all-reduced anyway so that no rank can leave the others waiting in the barrier below.
+        bad_groups = [names for names, flag in self._mask_flags if bool(flag.item())]
+        if _dist_on():
+            verdict = torch.tensor([1 if bad_groups else 0], device=device if torch.device(device).type == "cuda" else "cpu")
+            dist.all_reduce(verdict, op=dist.ReduceOp.MAX)
+            if bool(verdict.item()) and not bad_groups:
+                bad_groups = [["<reported by another rank>"]]
+        ops.set_timer(None)
+        if bad_groups:
+            raise RuntimeError(f"layers {bad_groups} share an input but have different all-zero weight columns: the results "
+                               f"written to {self.save_dir!r} for these layers are INVALID; rerun with share_hessians=False")
         if _dist_on():
             dist.barrier()
-        ops.set_timer(None)
 
     def non_invertible_modules(self) -> List[str]:
         """Modules whose Hessian was not positive definite (U fell back to identity, gptq.py:321-323). Synchronises."""

@@ -78,8 +78,8 @@ GQ_API long gq_launch_count(void);
 
 /* H <- beta*H + alpha * X^T X   -- replaces GPTQ.update's addmm_ (gptq.py:110-112).
  * X: (n_tok, d_col) of x_dtype, row-major, contiguous.  H: (d_col, d_col) fp32, kept fully symmetric.
- * bf16 inputs take the tcgen05 path (products exact in fp32, fp32 accumulation in TMEM);
- * other dtypes the fp32 SIMT path.  workspace: gq_hessian_workspace_bytes() bytes (may be 0). */
+ * 16-bit inputs (bf16 and fp16, d_col a multiple of 256) take the tcgen05 path (products exact in fp32, fp32 accumulation in
+ * TMEM); fp32 inputs the fp32 SIMT path.  workspace: gq_hessian_workspace_bytes() bytes (may be 0). */
 GQ_API size_t gq_hessian_workspace_bytes(long n_tok, int d_col, int x_dtype);
 GQ_API int gq_hessian_update(float *H, const void *X, long n_tok, int d_col, int x_dtype, float beta,
                       float alpha, void *workspace, size_t ws_bytes, gq_stream_t stream);
@@ -156,8 +156,9 @@ GQ_API int gq_rtn_quantize(const void *W, int w_dtype, int d_row, int d_col, int
                     void *qweight, uint16_t *d, void *sq, uint16_t *dmin, void *zq,
                     uint8_t *packed, void *wdeq, int wdeq_dtype, gq_stream_t stream);
 
-/* EXPERIMENTAL (not yet validated on hardware; the CPU oracle's twin is pinned to the reference, tests/golden/rtn_bf16.npz):
- * gq_rtn_quantize with the scale search in the arithmetic of the weight's own dtype, as the reference does it
+/* gq_rtn_quantize with the scale search in the arithmetic of the weight's own dtype, as the reference does it -- the driver's
+ * default for embed_tokens / lm_head of a 16-bit model (validated on B200 against the reference's own outputs,
+ * tests/golden/rtn_bf16.npz / rtn_f16.npz, tests/test_zz_gpu_rtn_native.py):
  * (quantizer.py:303-305 passes the weight un-widened): for GQ_BF16 / GQ_F16 every op of the search rounds to that dtype; the final
  * quantize() is fp32 as in the reference.  GQ_F32 falls through to gq_rtn_quantize.  Same arguments and outputs. */
 GQ_API int gq_rtn_quantize_native(const void *W, int w_dtype, int d_row, int d_col, int qtype,
