@@ -26,6 +26,7 @@ finish_wave() {
     [[ $failed -eq 0 ]] || { echo "a quantisation run failed, see $out/logs" >&2; exit 1; }
 }
 
+t_start=$(date +%s.%N)
 i=0
 for level in "${levels[@]}"; do
     gpu="${gpus[$((i % ${#gpus[@]}))]}"
@@ -38,7 +39,12 @@ for level in "${levels[@]}"; do
 done
 finish_wave
 
+t_quant=$(date +%s.%N)
 args=()
 for level in "${levels[@]}"; do args+=( --dir_model_quant "$out/$level" ); done
-python -m gptq_gguf_toolkit_b200.ep_database "$MODEL" "${args[@]}" --output_dir "$out/ep_database"
+# EP_DATABASE_ARGS: extra flags for the emitter, e.g. --no_hf_layers
+# shellcheck disable=SC2086
+python -m gptq_gguf_toolkit_b200.ep_database "$MODEL" "${args[@]}" --output_dir "$out/ep_database" ${EP_DATABASE_ARGS:-}
+t_end=$(date +%s.%N)
+echo "quantise_wall_s $(awk "BEGIN{print $t_quant - $t_start}")  database_wall_s $(awk "BEGIN{print $t_end - $t_quant}")"
 echo "database in $out/ep_database"

@@ -9,8 +9,12 @@
 namespace rk {
 constexpr int R = 32;        // rows per CTA
 constexpr int NT = 256;      // threads per CTA
-constexpr int KP = 16;       // k's per pipeline piece
-constexpr int S = 4;         // pipeline stages
+#ifndef GQ_RK_KP
+#define GQ_RK_KP 16
+#define GQ_RK_S 4
+#endif
+constexpr int KP = GQ_RK_KP; // k's per pipeline piece (one block-wide barrier per piece)
+constexpr int S = GQ_RK_S;   // pipeline stages
 constexpr int US_FLOATS = KP * 256;
 constexpr int ES_FLOATS = R * KP;
 }  // namespace rk
@@ -38,12 +42,12 @@ __device__ __forceinline__ void rank_update(float (&w)[8][4], const Params &p, f
             float *us = Us_base + st * US_FLOATS;
             float *es = Es_base + st * ES_FLOATS;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
+            for (int m = 0; m < KP / 4; ++m) {
                 const int id = tid + NT * m, row = id >> 6, c16 = id & 63;
                 if (!HALF || c16 >= 32) cp_async16(us + row * 256 + 4 * c16, U + (size_t)(k0 + row) * ld + c + 4 * c16);
             }
-            if (tid < 128) {
-                const int row = tid >> 2, part = tid & 3;
+            if (tid < R * (KP / 4)) {
+                const int row = tid / (KP / 4), part = tid % (KP / 4);
                 const int gr = min(r0 + row, p.d_row - 1);
                 cp_async16(es + row * KP + 4 * part, Wg + (size_t)gr * ld + k0 + 4 * part);
             }
@@ -83,7 +87,7 @@ __device__ __forceinline__ void rank_update(float (&w)[8][4], const Params &p, f
                 }
             }
         }
-        if ((pc & 7) == 7) {   // end of one earlier 128-column block: w <- w - acc  (gptq.py:270, alpha = -1)
+        if ((pc + 1) % (128 / KP) == 0) {   // end of one earlier 128-column block: w <- w - acc  (gptq.py:270, alpha = -1)
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll

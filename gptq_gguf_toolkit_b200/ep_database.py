@@ -40,10 +40,11 @@ def _prefix(qname: str) -> str:
     return f"{bw if bw != int(bw) else int(bw)}-{qname}"
 
 
-def emit_database(dir_model_quant: str, config, out_root: str, dtype: str = "float16") -> Dict[str, int]:
+def emit_database(dir_model_quant: str, config, out_root: str, dtype: str = "float16", hf_layers: bool = True) -> Dict[str, int]:
     """Emit `<out_root>/layers-gguf` and `<out_root>/layers-hf` for every module directory of `dir_model_quant`
     (the save_dir of quant.py).  Calling it once per quantisation level with the same `out_root` accumulates the levels
-    side by side, like the reference's loop over models.  Returns counts of files written."""
+    side by side, like the reference's loop over models.  hf_layers=False skips the fp16 HF-layout copies (the splitter's
+    --hf-layers switch; 16 GB per level for an 8B model).  Returns counts of files written."""
     cfg = config if isinstance(config, dict) else config.to_dict()
     n_layer, n_head = cfg["num_hidden_layers"], cfg["num_attention_heads"]
     n_kv = cfg.get("num_key_value_heads") or n_head
@@ -99,7 +100,7 @@ def emit_database(dir_model_quant: str, config, out_root: str, dtype: str = "flo
         counts["gguf"] += 1
         # ---- layers-hf: dequantised weight in HF row order (the splitter gets it from transformers' GGUF loader,
         # which undoes the q/k permutation), fp16; only the block projections (gguf_splitter.py:487-490)
-        if HF_LAYER_RE.match(module):
+        if hf_layers and HF_LAYER_RE.match(module):
             w = torch.from_numpy(gguf.quants.dequantize(np.ascontiguousarray(packed.numpy()), qtype)).to(tdtype)
             mdir = os.path.join(hdir, module)
             os.makedirs(mdir, exist_ok=True)
@@ -145,12 +146,13 @@ def main(argv: Optional[list] = None):
                     help="save_dir of quant.py; repeat the flag for several quantisation levels")
     ap.add_argument("--output_dir", type=str, required=True)
     ap.add_argument("--dtype", choices=["float16", "float32"], default="float16")
+    ap.add_argument("--no_hf_layers", action="store_true", help="only layers-gguf (the splitter without --hf-layers)")
     args = ap.parse_args(argv)
     from transformers import AutoConfig
     cfg = AutoConfig.from_pretrained(args.model)
     total = {"gguf": 0, "hf": 0}
     for d in args.dir_model_quant:
-        c = emit_database(d, cfg, args.output_dir, args.dtype)
+        c = emit_database(d, cfg, args.output_dir, args.dtype, hf_layers=not args.no_hf_layers)
         total = {k: total[k] + c[k] for k in total}
     print(json.dumps(total))
 

@@ -20,6 +20,7 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 import torch.nn as nn
+from torch.nn.modules.conv import _ConvNd
 
 from . import _lib as L
 from . import ops
@@ -76,10 +77,10 @@ class GPTQ:
                  mode: str = "exact", hessian: Optional[HessianAccumulator] = None):
         if act_order:
             assert static_groups                                            # gptq.py:45-46
-        assert isinstance(layer, nn.Linear), "libgq GPTQ supports nn.Linear layers"
+        assert isinstance(layer, (nn.Linear, _ConvNd)), "OBC supports only linear and convolutional layers."   # gptq.py:77
         self.layer = layer
         self.W = self.layer.weight
-        self.d_row, self.d_col = layer.weight.shape
+        self.d_row, self.d_col = layer.weight.shape[0], int(layer.weight[0].numel())      # model_utils.py:56-57
         self.rel_damp = rel_damp
         self.block_size = block_size or self.d_col                          # gptq.py:55
         self.act_order = act_order
@@ -109,7 +110,14 @@ class GPTQ:
 
     @torch.no_grad()
     def update(self, input: torch.Tensor) -> None:
-        """gptq.py:80-114."""
+        """gptq.py:80-114.  Convolutions: the input is unfolded into patches (rows = patches, columns = in_channels x kernel),
+        the batch still counts images (gptq.py:88, 97-107)."""
+        if isinstance(self.layer, _ConvNd):
+            unfold = nn.Unfold(self.layer.kernel_size, dilation=self.layer.dilation, padding=self.layer.padding,
+                               stride=self.layer.stride)
+            patches = unfold(input).transpose(1, 2)            # (batch, num_patches, channels * prod(kernel_size))
+            self.hessian.update(patches)
+            return
         self.hessian.update(input)
 
     def reset(self) -> None:
@@ -126,7 +134,7 @@ class GPTQ:
         """gptq.py:123-143."""
         assert self.H is not None, "One has to process at least one sample of calibration data to run pruning"
         self.hessian.all_reduce()
-        self.W = self.W.clone().float().contiguous()
+        self.W = self.W.clone().float().flatten(1, -1).contiguous()      # gptq.py:138-140 (convolutions: (out, in x kernel))
         if self.hessian.dead is None:
             self.hessian.dead = torch.diagonal(self.H) == 0     # bookkeeping for handles sharing this H
             ops.pre_step(self.H, self.W)

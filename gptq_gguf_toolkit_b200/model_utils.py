@@ -8,8 +8,13 @@ from typing import Any, Dict, List, Optional, Union
 import numpy as np
 import torch
 import torch.nn as nn
+from torch.nn.modules.conv import _ConvNd
 
-LINEAR_LAYERS = (nn.Linear,)
+LINEAR_LAYERS = (nn.Linear, _ConvNd)          # model_utils.py:12
+
+
+def get_number_of_rows_and_cols(layer):      # model_utils.py:56-57
+    return layer.weight.shape[0], int(np.prod(layer.weight.shape[1:]))
 
 
 class ForwardInterrupt(Exception):           # model_utils.py:14-15

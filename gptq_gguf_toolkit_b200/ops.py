@@ -142,11 +142,12 @@ def gptq_quantize(W: torch.Tensor, U: torch.Tensor, q_type: int, block_size: int
                   rdelta: float = 0.1, nstep: int = 20, mode: int = L.GQ_MODE_EXACT, packed: bool = True,
                   wdeq_dtype: Optional[torch.dtype] = None, search_flags: bool = False,
                   stream: Optional["torch.cuda.Stream"] = None, static_groups: bool = False,
-                  perm: Optional[torch.Tensor] = None):
+                  perm: Optional[torch.Tensor] = None, ws_slot: Optional[int] = None):
     """The column loop of one layer (gptq.py:146-295).  W: fp32 working copy in the ORIGINAL column order, CLOBBERED.
     Returns (qweight, d, sq, dmin, zq, packed|None, wdeq|None, flags|None), all in the original column order.
     stream: enqueue on this side stream (outputs are allocated on the CURRENT stream, which the side stream first
     waits for; the caller waits on the side stream before consuming the results).
+    ws_slot: scratch-buffer slot of GQ_MODE_FAST (default: 0 on the current stream, 100 on a side stream).
     static_groups (gptq.py:184-196): scales searched up front on W.  perm (act_order, gptq.py:209-216, needs
     static_groups): permutation of the columns, U must belong to H[perm][:, perm].  Q3_K ignores both (:204-206)."""
     L.require_cuda(W, U)
@@ -161,7 +162,8 @@ def gptq_quantize(W: torch.Tensor, U: torch.Tensor, q_type: int, block_size: int
     flags = torch.zeros(d_col // QK_K, 2, dtype=torch.int32, device=W.device) if search_flags else None
     lib = L.load()
     nws = lib.gq_gptq_workspace_bytes(d_row, d_col, int(mode))
-    ws = _workspace(W.device, nws, slot=100 if stream is not None else 0) if nws else None
+    # callers that run several column loops concurrently on different streams give each its own scratch slot
+    ws = _workspace(W.device, nws, slot=ws_slot if ws_slot is not None else (100 if stream is not None else 0)) if nws else None
     if stream is not None:
         stream.wait_stream(torch.cuda.current_stream(W.device))
     with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):

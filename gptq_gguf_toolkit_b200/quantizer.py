@@ -123,7 +123,8 @@ class Quantizer:
                  calibration_batch_size: int = 8, share_hessians: bool = True, keep_results: bool = False,
                  save_packed: bool = True, timer: Optional[PhaseTimer] = None, early_exit_pass1: bool = True,
                  overlap_prepare: bool = True, defer_last_layer: bool = True, fused_forward_ops: bool = True,
-                 early_prepare: bool = True, rtn_native_arith: bool = True, shard_prepare: bool = True) -> None:
+                 early_prepare: bool = True, rtn_native_arith: bool = True, shard_prepare: bool = True,
+                 concurrent_groups: bool = True) -> None:
         self.model = model
         self.data_loader = data_loader
         self.quantizable_modules = quantizable_modules
@@ -152,6 +153,11 @@ class Quantizer:
         # several ranks: every Cholesky chain (gq_prepare) of a block runs on ONE owner rank and U is broadcast, instead of
         # every rank running all of them (the reference factors on every rank too, gptq.py:305-324 is not rank-guarded)
         self.shard_prepare = shard_prepare
+        # the column loops of a block's groups (q/k/v, o, gate/up: different layers, nothing in common) run concurrently, each
+        # on its group's side stream right behind its Cholesky chain, instead of one after the other on the main stream: the
+        # serial panel -> update -> panel chains of the groups interleave and their CTA waves (192 + 128 + 896 CTAs of 32 rows on
+        # 148 SMs for Llama-3-8B) fill up together
+        self.concurrent_groups = concurrent_groups
         self.fused_installed: List[str] = []
         self._split_ok: Optional[bool] = None
         self._side_streams: list = []
@@ -358,7 +364,7 @@ class Quantizer:
         rows = [h.d_row for h in hs]
         side = self._side_stream(gi) if overlap else None
         # fp32 working copy of all members, stacked row-wise (gptq.py:138)
-        W = torch.cat([h.layer.weight.data.float() for h in hs], dim=0).contiguous()
+        W = torch.cat([h.layer.weight.data.float().flatten(1, -1) for h in hs], dim=0).contiguous()
         # With several ranks and a side stream the Hessian all-reduce and the dead-channel fix run on the side stream too
         # (their only consumer is the Cholesky chain behind them), so that the forward in flight on the main stream -- this
         # runs inside a hook of the last calibration batch -- is not held up by the collective.
@@ -438,10 +444,20 @@ class Quantizer:
         # With several ranks the all-gathers of a group's results run on a communication stream (_sharded_gptq), so the
         # next group's column loop does not wait for them: launch everything first, then wait once and finish in order.
         launched_all = []
+        conc = bool(self.concurrent_groups) and overlap and not staged and len(plans) > 1 and all(pl[7] is not None for pl in plans)
+        conc_events = []
         for plan in plans:
+            if conc:       # column loop on the group's own stream, right behind its chain (bit-neutral: same kernels, same inputs)
+                launched_all.append((plan, self._launch_group(plan, quant_config, rank, world, plan[7])))
+                ev = torch.cuda.Event()
+                ev.record(plan[7])
+                conc_events.append(ev)
+                continue
             if plan[6] is not None and not staged:
                 main.wait_event(plan[6])
             launched_all.append((plan, self._launch_group(plan, quant_config, rank, world, None)))
+        for ev in conc_events:
+            main.wait_event(ev)
         launched = ready = None
         if deferred is not None:
             # the deferred group: column loop on ITS side stream, right behind its Cholesky chain
@@ -494,7 +510,8 @@ class Quantizer:
             for i in idxs:
                 r1 = r0 + rows[i]
                 h = hs[i]
-                h.layer.weight.data = wdeq[r0:r1].clone() if len(idxs) > 1 else wdeq[r0:r1]
+                wnew = wdeq[r0:r1].clone() if len(idxs) > 1 else wdeq[r0:r1]
+                h.layer.weight.data = wnew.reshape(h.W_shape)      # convolutions keep their kernel shape
                 self._emit(names[i], qt, (qweight[r0:r1], d[r0:r1], sq[r0:r1], dmin[r0:r1], zq[r0:r1]),
                            packed[r0:r1] if packed is not None else None)
                 r0 = r1
@@ -513,9 +530,13 @@ class Quantizer:
 
     def _sharded_gptq(self, W, U, qt, dtype, rank, world, stream=None, static_groups=False, perm=None):
         kw = self.quantizer_kwargs
+        slot = None
+        if stream is not None and stream in self._side_streams:
+            slot = 100 + self._side_streams.index(stream)      # one fast-mode scratch buffer per concurrent column loop
         args = dict(block_size=kw.get("block_size", 128) or W.shape[1], rmin=kw.get("rmin", -1.0),
                     rdelta=kw.get("rdelta", 0.1), nstep=kw.get("nstep", 20), packed=True, wdeq_dtype=dtype,
-                    mode={"exact": 0, "fast": 1, "exact_left": 2, "exact_right": 3}[kw.get("mode", "exact")], static_groups=static_groups, perm=perm)
+                    mode={"exact": 0, "fast": 1, "exact_left": 2, "exact_right": 3}[kw.get("mode", "exact")], static_groups=static_groups, perm=perm,
+                    ws_slot=slot)
         if world == 1:
             return ops.gptq_quantize(W, U, qt, stream=stream, **args)[:7]
         # Row slice of this rank (in units of the kernel's 32-row CTA tile), then one all-gather per result tensor.

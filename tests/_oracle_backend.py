@@ -47,7 +47,7 @@ def prepare(H, W, rel_damp, stream=None, slot=0):
 
 
 def gptq_quantize(W, U, q_type, block_size=128, rmin=-1.0, rdelta=0.1, nstep=20, mode=0, packed=True, stream=None,
-                  wdeq_dtype=None, search_flags=False, static_groups=False, perm=None):
+                  wdeq_dtype=None, search_flags=False, static_groups=False, perm=None, ws_slot=None):
     out = orc.gptq_step(_np(W), _np(U), int(q_type), block_size, rmin, rdelta, nstep, static_groups=static_groups,
                         perm=None if perm is None else _np(perm))
     five = _five_t(out[:5])

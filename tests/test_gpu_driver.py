@@ -50,6 +50,8 @@ def test_scheduling_options_are_bit_neutral(dtype):
         "eager, no deferred tail": dict(defer_last_layer=False),
         "no early exit": dict(early_exit_pass1=False),
         "no early prepare (chains start after pass 1)": dict(early_prepare=False),
+        "column loops one after the other on the main stream": dict(concurrent_groups=False),
+        "fast mode scratch slots (concurrent groups)": dict(concurrent_groups=True, defer_last_layer=False),
     }
     for name, kw in variants.items():
         model, q = _run(dtype, **kw)

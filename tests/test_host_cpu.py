@@ -301,3 +301,31 @@ def test_world_size_2_gloo_row_sharding_and_allreduce(tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     assert json.loads(line)["ok"] is True
+
+
+def test_conv_layer_handle(monkeypatch):
+    """_ConvNd layers (model_utils.py:12, gptq.py:97-107, 139-140 of the reference): the Hessian is accumulated over unfolded
+    patches, the weight is flattened to (out_channels, in_channels x kernel), the batch counts images."""
+    from tests import _oracle_backend as ob
+    ob.install(monkeypatch)
+    from gptq_gguf_toolkit_b200.gptq import GPTQ
+    from gptq_gguf_toolkit_b200.model_utils import LINEAR_LAYERS, get_number_of_rows_and_cols
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(64, 24, kernel_size=2, stride=1, padding=1, bias=False)
+    assert isinstance(conv, LINEAR_LAYERS) and get_number_of_rows_and_cols(conv) == (24, 256)
+    h = GPTQ(conv, rel_damp=0.01, block_size=128)
+    assert (h.d_row, h.d_col) == (24, 256)
+    xs = [torch.randn(3, 64, 6, 5) for _ in range(2)]
+    H_ref = torch.zeros(256, 256, dtype=torch.float64)
+    n = 0
+    for x in xs:
+        h.update(x)
+        p = torch.nn.functional.unfold(x.double(), 2, padding=1).transpose(1, 2).flatten(0, 1)
+        H_ref = H_ref * (n / (n + 3)) + (2.0 / (n + 3)) * (p.T @ p)       # gptq.py:108-112 with batch_size = images
+        n += 3
+    assert h.num_samples == 6
+    assert torch.allclose(h.H.double(), H_ref, rtol=1e-5, atol=1e-5)
+    out = h.quantize(12)
+    assert out[0].shape == (24, 256) and h.wdeq.shape == (24, 256)
+    ref = orc.gptq_step(conv.weight.data.float().flatten(1).numpy(), h.hessian.U.numpy(), 12)
+    assert np.array_equal(out[0].numpy(), ref[0])
