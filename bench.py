@@ -318,14 +318,18 @@ def main():
 
     main_mode = "fast" if args.mode == "fast" else "exact"
     checks = {}
+    copy_stream = [None]
 
-    def result_checksums(results):
+    def result_crcs(results):
+        import zlib
+        return {n: zlib.crc32(memoryview(o["packed"].numpy()).cast("B")) & 0xFFFFFFFF for n, o in results.items() if "packed" in o}
+
+    def result_checksums(per):
         """CRC-32 of the packed GGUF bytes of every module as they arrived in host memory (outside the timed region).
         embed_tokens / lm_head (RTN, no calibration data) must be identical for every N; the GPTQ modules depend on the
         rounding of the Hessian all-reduce (gptq.py:131-132 averages per-rank sums), so their bytes agree across N only
         statistically -- in the reference as well."""
         import zlib
-        per = {n: zlib.crc32(memoryview(o["packed"].numpy()).cast("B")) & 0xFFFFFFFF for n, o in results.items() if "packed" in o}
         allc = 0
         for n in sorted(per):
             allc = zlib.crc32(per[n].to_bytes(4, "little"), allc)
@@ -364,13 +368,43 @@ def main():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         h2d = 0
+        hooks = []
         if e2e:
-            for n, m in mods.items():
-                m.weight.data = host_w[n].to(device, non_blocking=True)
-                h2d += host_w[n].numel() * host_w[n].element_size()
+            # Host weights stream in on a copy stream, in the order the quantiser needs them; a forward pre-hook per decoder block
+            # (and on embed_tokens) makes the compute stream wait for that block's weights only, so the 16 GB host -> device copy
+            # runs underneath the first blocks instead of in front of them.
+            copy = copy_stream[0] = copy_stream[0] or torch.cuda.Stream()      # ONE stream for all steps: the allocator pools per stream
+            main = torch.cuda.current_stream()
+            copy.wait_stream(main)
+            order = ["model.embed_tokens"] + [n for n in mods if n.startswith("model.layers.")] + [n for n in mods if n == "lm_head"]
+            events = {}
+            with torch.cuda.stream(copy):
+                for n in order:
+                    t = host_w[n].to(device, non_blocking=True)
+                    t.record_stream(main)
+                    mods[n].weight.data = t
+                    ev = torch.cuda.Event()
+                    ev.record(copy)
+                    events[n] = ev
+                    h2d += host_w[n].numel() * host_w[n].element_size()
+            layers = model.model.layers
+
+            def waiter(names):
+                def _h(_m, _a):
+                    for nm in names:
+                        torch.cuda.current_stream().wait_event(events[nm])
+                return _h
+            hooks.append(model.model.embed_tokens.register_forward_pre_hook(waiter(["model.embed_tokens"])))
+            for i, blk in enumerate(layers):
+                names_i = [n for n in mods if n.startswith(f"model.layers.{i}.")]
+                if i == len(layers) - 1:
+                    names_i = names_i + [n for n in mods if n == "lm_head"]
+                hooks.append(blk.register_forward_pre_hook(waiter(names_i)))
         q.quantize(quant_config)
         ev1.record()
         torch.cuda.synchronize()
+        for h in hooks:
+            h.remove()
         if world > 1:
             dist.barrier()
         secs = ev0.elapsed_time(ev1) / 1e3
@@ -382,9 +416,17 @@ def main():
         if e2e:
             for obj in q.results.values():
                 d2h += sum(v.numel() * v.element_size() for v in obj.values() if isinstance(v, torch.Tensor))
+            per = result_crcs(q.results)
+            if world > 1:      # the results are dealt out over the ranks (Quantizer.spread_emission)
+                t = torch.tensor([d2h], device=device, dtype=torch.int64)
+                dist.all_reduce(t)
+                d2h = int(t.item())
+                parts = [None] * world
+                dist.all_gather_object(parts, per)
+                per = {k: v for part in parts for k, v in part.items()}
             if rank == 0:
                 checks.clear()
-                checks.update(result_checksums(q.results))
+                checks.update(result_checksums(per))
             q.results.clear()
         bad = q.non_invertible_modules()
         return secs, timer.totals(), ops.launch_count() - l0, h2d, d2h, bad

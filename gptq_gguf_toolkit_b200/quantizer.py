@@ -12,7 +12,7 @@ What is different (B200-first, results unchanged):
   * multi-GPU (torch.distributed, NCCL): every rank holds its slice of the calibration sequences (as in the
     reference, quant.py:177-179), Hessians are all-reduced (gptq.py:131-132), then -- unlike the reference,
     where rank 0 quantises alone -- every rank quantises a ROW SLICE of each projection and the results are
-    all-gathered; rank 0 alone writes data.pth.
+    all-gathered; the data.pth files are written by the ranks in turn (`spread_emission`), or by rank 0 alone.
 """
 from __future__ import annotations
 
@@ -124,7 +124,7 @@ class Quantizer:
                  save_packed: bool = True, timer: Optional[PhaseTimer] = None, early_exit_pass1: bool = True,
                  overlap_prepare: bool = True, defer_last_layer: bool = True, fused_forward_ops: bool = True,
                  early_prepare: bool = True, rtn_native_arith: bool = True, shard_prepare: bool = True,
-                 concurrent_groups: bool = True) -> None:
+                 concurrent_groups: bool = True, spread_emission: bool = True) -> None:
         self.model = model
         self.data_loader = data_loader
         self.quantizable_modules = quantizable_modules
@@ -158,6 +158,11 @@ class Quantizer:
         # serial panel -> update -> panel chains of the groups interleave and their CTA waves (192 + 128 + 896 CTAs of 32 rows on
         # 148 SMs for Llama-3-8B) fill up together
         self.concurrent_groups = concurrent_groups
+        # several ranks: every rank holds every result after the all-gathers, so the device -> host copies and the data.pth
+        # writes of the modules are dealt out round-robin over the ranks (N PCIe links and N writer threads instead of rank 0's);
+        # the files are the same ones the reference's rank 0 writes (quantizer.py:120-128, 206-214, 267-275).  False: rank 0 only.
+        self.spread_emission = spread_emission
+        self._emit_counter = 0
         self.fused_installed: List[str] = []
         self._split_ok: Optional[bool] = None
         self._side_streams: list = []
@@ -182,8 +187,12 @@ class Quantizer:
 
     # -------------------------------------------------------------------------------------------
     def _emit(self, name: str, q_type, five, packed):
-        """data.pth schema of the reference (quantizer.py:267-275) + optional 'packed' GGUF bytes; rank 0 writes."""
-        if _rank() != 0:
+        """data.pth schema of the reference (quantizer.py:267-275) + optional 'packed' GGUF bytes; written by ONE rank: rank 0,
+        or with `spread_emission` the module's turn in a round-robin over the ranks (every rank calls this for every module in
+        the same order, so the counter agrees everywhere)."""
+        owner = (self._emit_counter % _world()) if self.spread_emission else 0
+        self._emit_counter += 1
+        if _rank() != owner:
             return
         if self.save_dir is None and not self.keep_results:
             return
@@ -711,7 +720,8 @@ class Quantizer:
         self._not_pd_flags = []
         self._mask_flags = []
         ops.set_timer(self.timer if self.timer.enabled else None)
-        if self.save_dir is not None and _rank() == 0:
+        self._emit_counter = 0
+        if self.save_dir is not None and (_rank() == 0 or self.spread_emission):
             os.makedirs(self.save_dir, exist_ok=True)
             self._saver = _AsyncSaver()
         blocks = self._get_submodule(self.block_modules)

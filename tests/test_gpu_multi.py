@@ -3,8 +3,8 @@
   * row sharding + all-gather (`Quantizer._sharded_gptq`), on the main stream and on a side stream (the deferred-tail
     variant), is bit-identical to the unsharded launch: rows of a GPTQ problem are independent given U;
   * a full driver run with the calibration sequences split over the ranks (quant.py:177-179 of the reference) leaves
-    IDENTICAL weights on every rank (pass 2 of every block runs on the all-gathered dequantised weights), emits results on
-    rank 0 only, and agrees with the single-rank run up to the rounding of the Hessian all-reduce (gptq.py:131-132 —
+    IDENTICAL weights on every rank (pass 2 of every block runs on the all-gathered dequantised weights), deals the results
+    out over the ranks (spread_emission: every module emitted exactly once), and agrees with the single-rank run up to the rounding of the Hessian all-reduce (gptq.py:131-132 —
     boundary B3, statistical: the summation order of H differs).
 """
 import json
@@ -78,7 +78,10 @@ per = len(seqs) // world
 m2, q2 = run(seqs[rank * per:(rank + 1) * per])                                  # default: eager chains + deferred tail
 m3, q3 = run(seqs[rank * per:(rank + 1) * per], defer_last_layer=False, overlap_prepare=False)
 res["deferred_tail_used"] = bool(q2._split_ok)
-res["results_on_rank0_only"] = (len(q2.results) == (3 * 7 + 2 if rank == 0 else 0))
+keys = [None] * world
+dist.all_gather_object(keys, sorted(q2.results))      # spread_emission: the modules' results are dealt out over the ranks
+res["results_partitioned_over_ranks"] = (len(set(sum(keys, []))) == 3 * 7 + 2 and sum(len(k) for k in keys) == 3 * 7 + 2
+                                          and all(len(k) >= (3 * 7 + 2) // world for k in keys))
 # every rank must hold the same weights afterwards, and the scheduling options must be bit-neutral at world 2 too
 same = True
 for (n, p), (_, p3) in zip(m2.named_parameters(), m3.named_parameters()):
@@ -95,19 +98,18 @@ Q._world, Q._rank, Q._dist_on = (lambda: 1), (lambda: 0), (lambda: False)
 G.HessianAccumulator.all_reduce = lambda self: setattr(self, "synced", True)
 m1, q1 = run(seqs)
 Q._world, Q._rank, Q._dist_on, G.HessianAccumulator.all_reduce = saved
-if rank == 0:
-    eq = tot = 0
-    num = den = 0.0
-    for name, r1 in q1.results.items():
-        a, b = r1["qweight"], q2.results[name]["qweight"]
-        eq += int((a == b).sum()); tot += a.numel()
-        w1, w2 = m1.get_submodule(name).weight.data.float(), m2.get_submodule(name).weight.data.float()
-        num += float((w1 - w2).pow(2).sum()); den += float(w1.pow(2).sum())
-    res["code_match_rate_vs_single_rank"] = eq / tot
-    res["rel_weight_diff_vs_single_rank"] = (num / den) ** 0.5
-    res["non_invertible"] = q2.non_invertible_modules()
-else:
-    q2.non_invertible_modules()
+eq = tot = 0
+num = den = 0.0
+for name, r2 in q2.results.items():          # this rank's share of the modules against the single-rank run
+    a, b = q1.results[name]["qweight"], r2["qweight"]
+    eq += int((a == b).sum()); tot += a.numel()
+    w1, w2 = m1.get_submodule(name).weight.data.float(), m2.get_submodule(name).weight.data.float()
+    num += float((w1 - w2).pow(2).sum()); den += float(w1.pow(2).sum())
+acc = torch.tensor([eq, tot, num, den], dtype=torch.float64, device=dev)
+dist.all_reduce(acc)
+res["code_match_rate_vs_single_rank"] = float(acc[0] / acc[1])
+res["rel_weight_diff_vs_single_rank"] = float((acc[2] / acc[3]) ** 0.5)
+res["non_invertible"] = q2.non_invertible_modules()
 dist.barrier()
 if rank == 0:
     print(json.dumps(res))
@@ -129,7 +131,7 @@ def test_world_size_2_nccl_driver_and_row_sharding(tmp_path):
     print(res)
     assert res["sharding_bit_exact"] is True
     assert res["deferred_tail_used"] is True
-    assert res["results_on_rank0_only"] is True
+    assert res["results_partitioned_over_ranks"] is True
     assert res["weights_identical_on_all_ranks"] is True
     assert res["non_invertible"] == []
     # B3-class agreement with the single-rank run: only the rounding of the Hessian average differs
