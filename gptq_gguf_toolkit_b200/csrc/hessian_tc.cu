@@ -6,14 +6,24 @@
 // GEMM of the widened inputs (only the summation order differs, which is unspecified in the reference too).
 //
 // Pipeline (one persistent CTA per SM, 256 threads, warp-specialised):
-//   transpose kernel : X (T x n) -> Xt (n x Tp), Tp = T rounded up to 64, zero padded  => both MMA operands K-major
+//   operands         : X (T x n, channels contiguous) is fed to the tensor cores AS IT IS, as MN-major operands (round 2): TMA boxes
+//                      of 64 tokens x 64 channels (128-byte rows, 128B swizzle) land as 1024-byte swizzle atoms of 64 channels x
+//                      8 tokens, SBO = 1024 B between token groups, LBO = 8192 B between 64-channel columns; tokens past T are
+//                      zero-filled by the TMA unit.  (GQ_HESSIAN_MN=0: round 1's path -- a transpose kernel writes Xt (n x Tp)
+//                      first so that both operands are K-major; 7-22 % slower and one more pass over the activations.)
 //   warp 0           : TMA producer, cp.async.bulk.tensor 2D, 128B swizzle, 4-stage mbarrier ring
 //                      stage = A tile 128 x 64 (16 KB) + B tile 256 x 64 (32 KB) of Xt
 //   warp 1           : one elected thread issues tcgen05.mma.cta_group::1.kind::f16, M128 N256 K16, accumulators
 //                      double-buffered in TMEM (2 x 256 columns) so the epilogue overlaps the next tile's MMAs
 //   warps 4-7        : epilogue: tcgen05.ld -> H = beta*H + alpha*acc, direct + mirrored store (H stays symmetric)
 // Only tiles that touch the upper triangle are computed (SYRK); strictly-lower elements come from the mirror.
+#include <cstdlib>
+
 #include "tc_common.cuh"
+
+#ifndef GQ_HESSIAN_MN_DEFAULT
+#define GQ_HESSIAN_MN_DEFAULT true
+#endif
 
 namespace {
 using namespace tc;
@@ -82,7 +92,7 @@ __global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t *__rest
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 1)
 hessian_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, float *H,
-                  int n, int nkb, int ntiles, float alpha, float beta, uint32_t idesc) {
+                  int n, int nkb, int ntiles, float alpha, float beta, uint32_t idesc, int mn_major) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     Barriers &bar = *reinterpret_cast<Barriers *>(smem + (size_t)STAGES * STAGE_BYTES);
@@ -118,8 +128,17 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     mbar_wait(&bar.empty[stage], phase ^ 1);
                     uint8_t *a = smem + (size_t)stage * STAGE_BYTES;
                     mbar_expect_tx(&bar.full[stage], STAGE_BYTES);
-                    tma_load_2d(a, &map_a, &bar.full[stage], kb * BK, tm * BM);
-                    tma_load_2d(a + A_BYTES, &map_b, &bar.full[stage], kb * BK, tn * BN);
+                    if (mn_major) {
+                        // X itself (tokens x channels): boxes of 64 tokens x 64 channels (128 B rows) -- two of them side by side
+                        // for the A tile's 128 channels, four for B's 256; tokens past T are zero-filled by the TMA unit
+#pragma unroll
+                        for (int c = 0; c < BM / 64; ++c) tma_load_2d(a + c * 8192, &map_a, &bar.full[stage], tm * BM + 64 * c, kb * BK);
+#pragma unroll
+                        for (int c = 0; c < BN / 64; ++c) tma_load_2d(a + A_BYTES + c * 8192, &map_a, &bar.full[stage], tn * BN + 64 * c, kb * BK);
+                    } else {
+                        tma_load_2d(a, &map_a, &bar.full[stage], kb * BK, tm * BM);
+                        tma_load_2d(a + A_BYTES, &map_b, &bar.full[stage], kb * BK, tn * BN);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -137,11 +156,20 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     mbar_wait(&bar.full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                    const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
-                    const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + A_BYTES);
+                    if (mn_major) {
+                        // MN-major operands: 64 channels x 8 tokens per 1024-byte swizzle atom, token groups 1024 B apart (SBO),
+                        // the next 64 channels 8192 B apart (LBO); a K step of 16 tokens = two token groups = 2048 B
+                        const uint64_t adesc = make_mnmajor_sw128_desc(a_addr), bdesc = make_mnmajor_sw128_desc(a_addr + A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k)   // +32 B per K step inside the 128 B swizzle span
-                        tc_mma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            tc_mma_f16(tmem_d, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (kb | k) != 0);
+                    } else {
+                        const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                        const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)   // +32 B per K step inside the 128 B swizzle span
+                            tc_mma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    }
                     tc_commit(&bar.empty[stage]);            // frees the smem stage when these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -214,6 +242,13 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// GQ_HESSIAN_MN=1: feed X (tokens x channels) to the tensor cores as MN-major operands, without the transposed copy
+// (read on every call: tests flip it).
+bool hessian_mn_major() {
+    const char *e = getenv("GQ_HESSIAN_MN");
+    return e ? e[0] == '1' : GQ_HESSIAN_MN_DEFAULT;
+}
+
 bool make_map(CUtensorMap *m, void *base, int dtype, uint64_t rows, uint64_t cols_padded, uint32_t box_rows) {
     const CUtensorMapDataType dt = dtype == GQ_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     return make_map_2d(m, base, dt, 2, rows, cols_padded, BK, box_rows);
@@ -222,6 +257,7 @@ bool make_map(CUtensorMap *m, void *base, int dtype, uint64_t rows, uint64_t col
 }  // namespace
 
 size_t gq_hessian_tc_workspace_bytes(long n_tok, int d_col) {
+    if (hessian_mn_major()) return 0;      // the tensor map covers X itself
     const long Tp = (n_tok + BK - 1) / BK * BK;
     return (size_t)d_col * (size_t)Tp * 2 + 1024;
 }
@@ -232,32 +268,42 @@ bool gq_hessian_tc_supported(long n_tok, int d_col, int x_dtype) {
 
 int gq_hessian_tc(float *H, const void *X, long n_tok, int d_col, int x_dtype, float beta, float alpha, void *workspace,
                   size_t ws_bytes, cudaStream_t st) {
-    if (ws_bytes < gq_hessian_tc_workspace_bytes(n_tok, d_col) || workspace == nullptr) {
+    if (ws_bytes < gq_hessian_tc_workspace_bytes(n_tok, d_col) || (workspace == nullptr && !hessian_mn_major())) {
         gq_set_error("gq_hessian_update: workspace %zu < %zu bytes", ws_bytes, gq_hessian_tc_workspace_bytes(n_tok, d_col));
         return GQ_ERR_WORKSPACE;
     }
     const int n = d_col, T = (int)n_tok;
     const int Tp = (T + BK - 1) / BK * BK;
-    uint16_t *Xt = reinterpret_cast<uint16_t *>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
-    {
+    const bool mn = hessian_mn_major();
+    CUtensorMap map_a, map_b;
+    if (mn) {
+        // no transposed copy: the tensor map covers X itself, (T rows of n channels), boxes of 64 channels x 64 tokens
+        const CUtensorMapDataType dt = x_dtype == GQ_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+        if (!make_map_2d(&map_a, const_cast<void *>(X), dt, 2, (uint64_t)T, (uint64_t)n, 64, 64)) {
+            gq_set_error("gq_hessian_update: cuTensorMapEncodeTiled failed");
+            return GQ_ERR_CUDA;
+        }
+        map_b = map_a;
+    } else {
+        uint16_t *Xt = reinterpret_cast<uint16_t *>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
         dim3 grid(Tp / 64, n / 64);
         transpose16_kernel<<<grid, 256, 0, st>>>((const uint16_t *)X, Xt, T, n, Tp);
         gq_count_launches(1);
-    }
-    CUtensorMap map_a, map_b;
-    if (!make_map(&map_a, Xt, x_dtype, (uint64_t)n, (uint64_t)Tp, BM) || !make_map(&map_b, Xt, x_dtype, (uint64_t)n, (uint64_t)Tp, BN)) {
-        gq_set_error("gq_hessian_update: cuTensorMapEncodeTiled failed");
-        return GQ_ERR_CUDA;
+        if (!make_map(&map_a, Xt, x_dtype, (uint64_t)n, (uint64_t)Tp, BM) || !make_map(&map_b, Xt, x_dtype, (uint64_t)n, (uint64_t)Tp, BN)) {
+            gq_set_error("gq_hessian_update: cuTensorMapEncodeTiled failed");
+            return GQ_ERR_CUDA;
+        }
     }
     const int ntm = n / BM, ntn = n / BN;
     int ntiles = 0;
     for (int m = 0; m < ntm; ++m) ntiles += ntn - (m >> 1);
     const uint32_t fmt = x_dtype == GQ_BF16 ? 1u : 0u;
     // kind::f16 instruction descriptor: D = F32, A/B = fmt, both K-major, N = 256, M = 128
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    if (mn) idesc |= (1u << 15) | (1u << 16);      // A and B are MN-major (the channel index is the contiguous one)
     GQ_CHECK_CUDA(cudaFuncSetAttribute(hessian_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     const int grid = ntiles < num_sms() ? ntiles : num_sms();
-    hessian_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(map_a, map_b, H, n, Tp / BK, ntiles, alpha, beta, idesc);
+    hessian_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(map_a, map_b, H, n, Tp / BK, ntiles, alpha, beta, idesc, mn ? 1 : 0);
     gq_count_launches(1);
     GQ_CHECK_CUDA(cudaGetLastError());
     return GQ_OK;

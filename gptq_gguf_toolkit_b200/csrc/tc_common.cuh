@@ -71,6 +71,19 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 }
 
 
+// MN-major, 128-byte-swizzled operand tile of 16-bit elements: 64 elements of the M / N axis are contiguous (128 B), 8 consecutive
+// K indices make one 1024-byte swizzle atom; SBO = distance between atoms along K (1024 B when a 64-wide column of atoms is stored
+// contiguously), LBO = distance between atoms along M / N (8192 B for 64 K indices per stage).
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes = 8192, uint32_t sbo_bytes = 1024) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
 // kind::tf32 variant of tc_mma_f16 (fp32 containers, 10-bit mantissa used by the tensor core)
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"

@@ -3,7 +3,7 @@
 tag=${1:-r02h}
 mkdir -p gpurun_out
 for n in 8 4; do
-  extra="--no-e2e"; [ $n = 8 ] && extra=""
+  extra=""
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2955$n \
       bench.py --gpus $n --steps 1 --warmup 2 --mode exact $extra > gpurun_out/${tag}_bench_n$n.json 2> gpurun_out/${tag}_bench_n$n.err
   echo "n$n exit $?"

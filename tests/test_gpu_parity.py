@@ -244,7 +244,15 @@ def test_pack_dequant_golden_and_gguf_py(ops, golden_dir, tname):
 # ------------------------------------------------------------------------------------------------
 # Hessian and Cholesky chain (floating point: tolerance stated in each test)
 # ------------------------------------------------------------------------------------------------
-def test_hessian_tensor_core_path_large(ops):
+@pytest.fixture(params=["1", "0"], ids=["mn_major_operands", "transposed_copy"])
+def hessian_path(request, monkeypatch):
+    """Both operand paths of hessian_tc.cu: X fed as MN-major operands straight from the activations (the default since round 2)
+    and round 1's transposed K-major copy (GQ_HESSIAN_MN=0); the library reads the variable on every call."""
+    monkeypatch.setenv("GQ_HESSIAN_MN", request.param)
+    return request.param
+
+
+def test_hessian_tensor_core_path_large(ops, hessian_path):
     """tcgen05 SYRK at a Llama-sized d_col: several tiles per CTA, both TMEM accumulator buffers, k tail padding."""
     torch.manual_seed(3)
     d_col, T = 4096, 4096 + 40
@@ -261,7 +269,7 @@ def test_hessian_tensor_core_path_large(ops):
 
 @pytest.mark.parametrize("d_col", [384, 512, 1280])
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
-def test_hessian_update(ops, dt, d_col):
+def test_hessian_update(ops, dt, d_col, hessian_path):
     torch.manual_seed(0)
     H = torch.zeros(d_col, d_col, device="cuda")
     ref = torch.zeros(d_col, d_col, dtype=torch.float64)
