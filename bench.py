@@ -142,9 +142,9 @@ REFERENCE_MEASURED = {
 
 
 def cpu_reference_sample(w, threads: int):
-    """Times a bounded sample (~30 s of CPU work) and extrapolates each phase by its algorithmic work to the whole model.
-    Returns (whole_model_hot_path_seconds, detail).  Sample: 8 sequences of H.addmm_ and one Cholesky chain at every distinct
-    d_col, the column loop on WHOLE-WIDTH slabs (512 rows at the narrow width, 128 rows at the widest)."""
+    """Times a bounded sample (~10-30 s of CPU work, depending on the host's cores) and extrapolates each phase by its algorithmic
+    work to the whole model.  Returns (whole_model_hot_path_seconds, detail).  Sample: 16 sequences of H.addmm_ and one Cholesky chain at every distinct
+    d_col, the column loop on WHOLE-WIDTH slabs (2048 rows at the narrow width, 512 rows at the widest)."""
     from oracle import oracle as orc
     import numpy as np
     torch.set_num_threads(threads)
@@ -156,7 +156,7 @@ def cpu_reference_sample(w, threads: int):
     detail, sample_s = {}, {}
     # 1. Hessian: H.addmm_ per calibration sequence (gptq.py:108-112), 8 sequences at every distinct d_col
     t_h = {}
-    n_h = min(8, nseq)
+    n_h = min(16, nseq)
     for c in dcols:
         x = torch.randn(L, c, generator=g).to(torch.bfloat16).float()
         H = torch.zeros(c, c)
@@ -184,7 +184,7 @@ def cpu_reference_sample(w, threads: int):
     #    on a slab of the layer's FULL width at every distinct d_col
     t_row = {}
     for c in dcols:
-        rows = 512 if c <= 4096 else 128
+        rows = 2048 if c <= 4096 else 512
         rng = np.random.default_rng(c)
         W = (rng.standard_normal((rows, c)) * 0.02).astype(np.float32)
         U = np.triu(rng.standard_normal((c, c)).astype(np.float32) * 0.01) + np.eye(c, dtype=np.float32)
@@ -200,8 +200,8 @@ def cpu_reference_sample(w, threads: int):
     return total, detail
 
 
-CPU_SAMPLE_NOTE = ("per phase: H.addmm_ of 8 sequences of 2048 tokens at each d_col, one Cholesky chain (cholesky, cholesky_inverse, "
-                   "cholesky upper) at each d_col, the column loop on whole-width slabs (512 rows x 4096, 128 rows x 14336); scaled by "
+CPU_SAMPLE_NOTE = ("per phase: H.addmm_ of 16 sequences of 2048 tokens at each d_col, one Cholesky chain (cholesky, cholesky_inverse, "
+                   "cholesky upper) at each d_col, the column loop on whole-width slabs (2048 rows x 4096, 512 rows x 14336); scaled by "
                    "algorithmic work to 32 blocks x 7 projections x 128 sequences -- EXTRAPOLATED, hot path only (no model forwards, "
                    "no embed/lm_head), oracle PORT of the reference (see reference_measured for the reference's own functions)")
 

@@ -184,6 +184,14 @@ def gptq_quantize(W: torch.Tensor, U: torch.Tensor, q_type: int, block_size: int
                 sg, L.ptr(pm), L.ptr(qk), L.ptr(d), L.ptr(sq), L.ptr(dmin), L.ptr(zq), L.ptr(pk), L.ptr(wd),
                 L.dtype_code(wdeq_dtype) if (wdeq_dtype is not None and fused) else 0, L.ptr(flags), L.ptr(ws), nws,
                 L.stream_of(W.device)))
+            if stream is not None:
+                # inputs / temporaries that were allocated on the CURRENT stream and are read by the kernels just enqueued on
+                # `stream`: a caller may drop its last reference (a stacked sub-matrix built for this call, the permuted copies)
+                # as soon as this function returns, and the caching allocator would hand the memory to the current stream's next
+                # allocation underneath the running kernel
+                for t in (W, Wk, qk, pm, U):
+                    if t is not None:
+                        t.record_stream(stream)
             if perm is not None:
                 qweight.index_copy_(1, perm, qk)                    # gptq.py:276-277: qweight[:, invperm]
                 pk = pack(q_type, qweight, d, sq, dmin, zq) if packed else None
