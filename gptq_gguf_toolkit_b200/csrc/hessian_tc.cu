@@ -240,6 +240,194 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------
+// cta_group::2 variant (the default; GQ_HESSIAN_2CTA=0 selects the one-CTA kernel above): a CTA PAIR owns a (256 x 256) tile.  Each CTA stages its own 128 channels of A and
+// HALF of B (128 of the 256 channels): 32 KB per stage instead of 48 KB, i.e. a third less L2 -> shared-memory traffic per
+// flop, and a 6-stage ring.  The leader CTA's one thread issues tcgen05.mma.cta_group::2 (M = 256: each CTA's tensor core
+// computes its 128 rows into its own TMEM, reading the other half of B from the peer's shared memory); TMA loads of both CTAs
+// complete on the LEADER's full barrier, the MMA commits are multicast to both CTAs' empty / accumulator-full barriers, and the
+// epilogue warps of both CTAs release the accumulator on the leader's barrier.  Measured on B200 per 16384 tokens: n = 4096
+// 0.251 -> 0.226 ms, n = 14336 2.98 -> 2.67 ms (1.26 PFLOP/s of upper-triangle flops).
+// ---------------------------------------------------------------------------------------------
+constexpr int STAGES2 = 6;
+constexpr int STAGE2_BYTES = 4 * 8192;            // 2 boxes (64 tokens x 64 channels) of A + 2 of B
+struct Barriers2 {
+    uint64_t full[STAGES2];
+    uint64_t empty[STAGES2];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+};
+constexpr size_t SMEM2_BYTES = 1024 + (size_t)STAGES2 * STAGE2_BYTES + sizeof(Barriers2);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p`'s counterpart in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void *p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void tma_load_2d_2cta(void *dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2cta(uint64_t *bar) {      // arrives on `bar` (same offset) in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+// pair tiles: (tm2, tn) over 256-row / 256-column blocks with tn >= tm2 (upper triangle)
+__device__ __forceinline__ void tile_coords2(int idx, int ntn, int &tm2, int &tn) {
+    int m = 0;
+    while (idx >= ntn - m) { idx -= ntn - m; ++m; }
+    tm2 = m;
+    tn = m + idx;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+hessian_tc2_kernel(const __grid_constant__ CUtensorMap map_x, float *H, int n, int nkb, int ntiles, float alpha, float beta,
+                   uint32_t idesc) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    Barriers2 &bar = *reinterpret_cast<Barriers2 *>(smem + (size_t)STAGES2 * STAGE2_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntn = n / 256;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(&bar.full[s], 1); mbar_init(&bar.empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&bar.tmem_full[b], 1); mbar_init(&bar.tmem_empty[b], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bar.tmem_base)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = bar.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {   // ===== TMA producer (both CTAs; transactions complete on the leader's full barrier) =====
+            int stage = 0, phase = 0;
+            for (int t = pair; t < ntiles; t += npairs) {
+                int tm2, tn;
+                tile_coords2(t, ntn, tm2, tn);
+                const int a_ch = tm2 * 256 + (int)rank * 128, b_ch = tn * 256 + (int)rank * 128;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&bar.empty[stage], phase ^ 1);
+                    uint8_t *a = smem + (size_t)stage * STAGE2_BYTES;
+                    const uint32_t full0 = mapa_u32(&bar.full[stage], 0);
+                    if (rank == 0) mbar_expect_tx(&bar.full[stage], 2 * STAGE2_BYTES);
+                    tma_load_2d_2cta(a, &map_x, full0, a_ch, kb * BK);
+                    tma_load_2d_2cta(a + 8192, &map_x, full0, a_ch + 64, kb * BK);
+                    tma_load_2d_2cta(a + 16384, &map_x, full0, b_ch, kb * BK);
+                    tma_load_2d_2cta(a + 24576, &map_x, full0, b_ch + 64, kb * BK);
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {   // ===== MMA issuer (leader CTA only) =====
+            int stage = 0, phase = 0, it = 0;
+            for (int t = pair; t < ntiles; t += npairs, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&bar.tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * 256;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&bar.full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + (size_t)stage * STAGE2_BYTES);
+                    const uint64_t adesc = make_mnmajor_sw128_desc(a_addr), bdesc = make_mnmajor_sw128_desc(a_addr + 16384);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        tc_mma_f16_2cta(tmem_d, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (kb | k) != 0);
+                    tc_commit_2cta(&bar.empty[stage]);
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                }
+                tc_commit_2cta(&bar.tmem_full[buf]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (both CTAs): own TMEM (128 rows of the pair's tile) -> H, direct + mirrored =====
+        const int q = warp & 3;
+        int it = 0;
+        for (int t = pair; t < ntiles; t += npairs, ++it) {
+            int tm2, tn;
+            tile_coords2(t, ntn, tm2, tn);
+            const int buf = it & 1;
+            mbar_wait(&bar.tmem_full[buf], (it >> 1) & 1);
+            tc_fence_after();
+            const int i_lo = tm2 * 256 + (int)rank * 128 + q * 32, i = i_lo + lane, i_hi = i_lo + 31;
+            float *hrow = H + (size_t)i * n;
+#pragma unroll 1
+            for (int ch = 0; ch < 256 / 32; ++ch) {
+                const int j0 = tn * 256 + ch * 32;
+                if (j0 + 31 < i_lo) continue;
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + ch * 32), v);
+                const bool all_upper = (j0 >= i_hi);
+                if (all_upper) {
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (beta != 0.0f) h = *reinterpret_cast<const float4 *>(hrow + j0 + 4 * c4);
+                        float4 o;
+                        o.x = __fmaf_rn(alpha, __uint_as_float(v[4 * c4 + 0]), __fmul_rn(beta, h.x));
+                        o.y = __fmaf_rn(alpha, __uint_as_float(v[4 * c4 + 1]), __fmul_rn(beta, h.y));
+                        o.z = __fmaf_rn(alpha, __uint_as_float(v[4 * c4 + 2]), __fmul_rn(beta, h.z));
+                        o.w = __fmaf_rn(alpha, __uint_as_float(v[4 * c4 + 3]), __fmul_rn(beta, h.w));
+                        *reinterpret_cast<float4 *>(hrow + j0 + 4 * c4) = o;
+                        v[4 * c4 + 0] = __float_as_uint(o.x); v[4 * c4 + 1] = __float_as_uint(o.y);
+                        v[4 * c4 + 2] = __float_as_uint(o.z); v[4 * c4 + 3] = __float_as_uint(o.w);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (j0 + c != i) H[(size_t)(j0 + c) * n + i] = __uint_as_float(v[c]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int j = j0 + c;
+                        if (j >= i) {
+                            const float h = (beta != 0.0f) ? hrow[j] : 0.0f;
+                            const float o = __fmaf_rn(alpha, __uint_as_float(v[c]), __fmul_rn(beta, h));
+                            hrow[j] = o;
+                            if (j != i) H[(size_t)j * n + i] = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(&bar.tmem_empty[buf], 0));
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 // GQ_HESSIAN_MN=1: feed X (tokens x channels) to the tensor cores as MN-major operands, without the transposed copy
@@ -247,6 +435,11 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 bool hessian_mn_major() {
     const char *e = getenv("GQ_HESSIAN_MN");
     return e ? e[0] == '1' : GQ_HESSIAN_MN_DEFAULT;
+}
+
+bool hessian_2cta() {      // GQ_HESSIAN_2CTA=0: one CTA per tile (round 2's first MN-major kernel); default: the cta_group::2 kernel
+    const char *e = getenv("GQ_HESSIAN_2CTA");
+    return e ? e[0] == '1' : true;
 }
 
 bool make_map(CUtensorMap *m, void *base, int dtype, uint64_t rows, uint64_t cols_padded, uint32_t box_rows) {
@@ -293,6 +486,21 @@ int gq_hessian_tc(float *H, const void *X, long n_tok, int d_col, int x_dtype, f
             gq_set_error("gq_hessian_update: cuTensorMapEncodeTiled failed");
             return GQ_ERR_CUDA;
         }
+    }
+    if (mn && hessian_2cta()) {
+        const int ntn2 = n / 256;
+        const int npair_tiles = ntn2 * (ntn2 + 1) / 2;
+        const uint32_t fmt2 = x_dtype == GQ_BF16 ? 1u : 0u;
+        // kind::f16, D = F32, A / B = fmt (MN-major), N = 256, M = 256 (the CTA pair's tile)
+        const uint32_t idesc2 = (1u << 4) | (fmt2 << 7) | (fmt2 << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(256 >> 3) << 17) |
+                                ((uint32_t)(256 >> 4) << 24);
+        GQ_CHECK_CUDA(cudaFuncSetAttribute(hessian_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2_BYTES));
+        const int max_pairs = num_sms() / 2;
+        const int pairs = npair_tiles < max_pairs ? npair_tiles : max_pairs;
+        hessian_tc2_kernel<<<2 * pairs, NTHREADS, SMEM2_BYTES, st>>>(map_a, H, n, Tp / BK, npair_tiles, alpha, beta, idesc2);
+        gq_count_launches(1);
+        GQ_CHECK_CUDA(cudaGetLastError());
+        return GQ_OK;
     }
     const int ntm = n / BM, ntn = n / BN;
     int ntiles = 0;

@@ -244,11 +244,13 @@ def test_pack_dequant_golden_and_gguf_py(ops, golden_dir, tname):
 # ------------------------------------------------------------------------------------------------
 # Hessian and Cholesky chain (floating point: tolerance stated in each test)
 # ------------------------------------------------------------------------------------------------
-@pytest.fixture(params=["1", "0"], ids=["mn_major_operands", "transposed_copy"])
+@pytest.fixture(params=[("1", "1"), ("1", "0"), ("0", "0")], ids=["mn_major_2cta", "mn_major_1cta", "transposed_copy"])
 def hessian_path(request, monkeypatch):
-    """Both operand paths of hessian_tc.cu: X fed as MN-major operands straight from the activations (the default since round 2)
-    and round 1's transposed K-major copy (GQ_HESSIAN_MN=0); the library reads the variable on every call."""
-    monkeypatch.setenv("GQ_HESSIAN_MN", request.param)
+    """The three kernels of hessian_tc.cu: X fed as MN-major operands straight from the activations to a cta_group::2 kernel (CTA
+    pairs on 256 x 256 tiles; the default since round 2), the same operands on one CTA per 128 x 256 tile (GQ_HESSIAN_2CTA=0), and
+    round 1's transposed K-major copy (GQ_HESSIAN_MN=0); the library reads the variables on every call."""
+    monkeypatch.setenv("GQ_HESSIAN_MN", request.param[0])
+    monkeypatch.setenv("GQ_HESSIAN_2CTA", request.param[1])
     return request.param
 
 
