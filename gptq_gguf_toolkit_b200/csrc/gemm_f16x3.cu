@@ -16,8 +16,11 @@
 //     accumulators (2 x 256 columns) so that a tile's epilogue -- C is read and written in full 128-byte lines through a
 //     shared-memory transpose, its reads issued before the accumulator is waited for -- runs under the next tile's MMAs.
 // Users: the rank-k update of GQ_MODE_FAST (gptq_layer.cu) and, with 128-wide tiles, the Cholesky chain (linalg.cu).
+#include <cstdlib>
+
 #include "gemm_f16x3.cuh"
 #include "tc_common.cuh"
+
 
 namespace {
 using namespace tc;
@@ -235,6 +238,189 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------
+// cta_group::2 variant for the big rank-k updates (TM_FULL / KM_FULL, M and N multiples of 256): a CTA PAIR owns a 256 x 256
+// tile.  Each CTA stages its own 128 rows of A and HALF of B (128 of the 256 rows): 32 KB per stage instead of 48 KB -- a third
+// less L2 -> shared-memory operand traffic per flop -- in a 6-stage ring; the leader's one thread issues
+// tcgen05.mma.cta_group::2 (M = 256), TMA transactions of both CTAs complete on the leader's full barrier, MMA commits are
+// multicast to both CTAs, and the epilogue warps of both CTAs (each on its own 128 rows in its own TMEM) release the
+// accumulator on the leader's barrier.  Same protocol as hessian_tc2_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int STAGES2 = 6, STAGE2_BYTES = 2 * BM * ROW_BYTES;       // A (128 rows) + half of B (128 rows)
+constexpr size_t SMEM2_BYTES = 1024 + (size_t)STAGES2 * STAGE2_BYTES + BAR_BYTES + (size_t)EPI_WARPS * EPI_STAGE_BYTES;
+static_assert(SMEM2_BYTES <= 232448, "shared memory budget (2-CTA kernel)");
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(const void *p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void tma_load_2d_2cta(void *dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2cta(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+gemm_f16x3_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const KParams p) {
+    constexpr int BN = 256, CH = 4;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    Barriers &bar = *reinterpret_cast<Barriers *>(smem + (size_t)STAGES2 * STAGE2_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int ntn = p.N / 256, ntiles = (p.M / 256) * ntn;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(&bar.full[s], 1); mbar_init(&bar.empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&bar.tmem_full[b], 1); mbar_init(&bar.tmem_empty[b], 2 * EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bar.tmem_base)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = bar.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {   // ===== TMA producer (both CTAs) =====
+            int stage = 0, phase = 0;
+            for (int t = pair; t < ntiles; t += npairs) {
+                const int tm2 = t / ntn, tn = t - tm2 * ntn;
+                const int arow = p.a_row0 + tm2 * 256 + (int)rank * 128, brow = p.b_row0 + tn * 256 + (int)rank * 128;
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(&bar.empty[stage], phase ^ 1);
+                    uint8_t *s = smem + (size_t)stage * STAGE2_BYTES;
+                    const uint32_t full0 = mapa_u32(&bar.full[stage], 0);
+                    if (rank == 0) mbar_expect_tx(&bar.full[stage], 2 * STAGE2_BYTES);
+                    tma_load_2d_2cta(s, &map_a, full0, (p.a_kb0 + kb) * 64, arow);
+                    tma_load_2d_2cta(s + BM * ROW_BYTES, &map_b, full0, (p.b_kb0 + kb) * 64, brow);
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {   // ===== MMA issuer (leader CTA) =====
+            int stage = 0, phase = 0, it = 0;
+            for (int t = pair; t < ntiles; t += npairs, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&bar.tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * BN;
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(&bar.full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t s = smem_u32(smem + (size_t)stage * STAGE2_BYTES);
+                    const uint64_t ad = make_kmajor_sw128_desc(s), bd = make_kmajor_sw128_desc(s + BM * ROW_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t h = (uint64_t)(2 * k), l = (uint64_t)(2 * k + 4);
+                        tc_mma_f16_2cta(tmem_d, ad + l, bd + h, p.idesc, (kb > 0) || (k > 0));
+                        tc_mma_f16_2cta(tmem_d, ad + h, bd + l, p.idesc, 1);
+                        tc_mma_f16_2cta(tmem_d, ad + h, bd + h, p.idesc, 1);
+                    }
+                    tc_commit_2cta(&bar.empty[stage]);
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                }
+                tc_commit_2cta(&bar.tmem_full[buf]);
+            }
+        }
+    } else if (warp >= 4) {   // ===== epilogue (both CTAs, each on its 128 rows of the pair's tile) =====
+        const int ew = warp - 4, q = warp & 3, half = ew >> 2;
+        float *stage = reinterpret_cast<float *>(smem + (size_t)STAGES2 * STAGE2_BYTES + BAR_BYTES) + ew * (EPI_STAGE_BYTES / 4);
+        const int rr = lane >> 3, jj = lane & 7;
+        int it = 0;
+        for (int t = pair; t < ntiles; t += npairs, ++it) {
+            const int tm2 = t / ntn, tn = t - tm2 * ntn;
+            const int buf = it & 1;
+            const int m0 = tm2 * 256 + (int)rank * 128 + q * 32;
+            const int n0 = tn * BN + half * (BN / 2);
+            float *cbase = p.C + (long)m0 * p.ldc + n0 + 4 * jj;
+            const float sa = p.sa ? p.sa[p.a_row0 + m0 + lane] : 1.0f;
+            const float *sbp = p.sb ? p.sb + p.b_row0 + n0 + 4 * jj : nullptr;
+            float4 cbuf[2][8];
+            auto load_c = [&](float4 (&dst)[8], int cc) {
+#pragma unroll
+                for (int i8 = 0; i8 < 8; ++i8) {
+                    const int r = 4 * i8 + rr;
+                    dst[i8] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.beta != 0.0f && m0 + r < p.m_valid)
+                        dst[i8] = *reinterpret_cast<const float4 *>(cbase + (long)r * p.ldc + cc * 32);
+                }
+            };
+            load_c(cbuf[0], 0);
+            load_c(cbuf[1], 1);
+            mbar_wait(&bar.tmem_full[buf], (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < CH; ++cc) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * (BN / 2) + cc * 32), v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4 *>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                        make_float4(__fmul_rn(sa, __uint_as_float(v[4 * j])), __fmul_rn(sa, __uint_as_float(v[4 * j + 1])),
+                                    __fmul_rn(sa, __uint_as_float(v[4 * j + 2])), __fmul_rn(sa, __uint_as_float(v[4 * j + 3])));
+                __syncwarp();
+                float4 s4 = make_float4(p.alpha, p.alpha, p.alpha, p.alpha);
+                if (sbp) {
+                    const float4 t4 = *reinterpret_cast<const float4 *>(sbp + cc * 32);
+                    s4 = make_float4(__fmul_rn(p.alpha, t4.x), __fmul_rn(p.alpha, t4.y), __fmul_rn(p.alpha, t4.z), __fmul_rn(p.alpha, t4.w));
+                }
+#pragma unroll
+                for (int i8 = 0; i8 < 8; ++i8) {
+                    const int r = 4 * i8 + rr;
+                    const float4 a = *reinterpret_cast<const float4 *>(stage + r * 32 + ((jj ^ (r & 7)) << 2));
+                    const float4 h = cbuf[cc & 1][i8];
+                    float4 o;
+                    o.x = __fmaf_rn(s4.x, a.x, __fmul_rn(p.beta, h.x));
+                    o.y = __fmaf_rn(s4.y, a.y, __fmul_rn(p.beta, h.y));
+                    o.z = __fmaf_rn(s4.z, a.z, __fmul_rn(p.beta, h.z));
+                    o.w = __fmaf_rn(s4.w, a.w, __fmul_rn(p.beta, h.w));
+                    if (m0 + r < p.m_valid) *reinterpret_cast<float4 *>(cbase + (long)r * p.ldc + cc * 32) = o;
+                }
+                __syncwarp();
+                if (cc + 2 < CH) load_c(cbuf[cc & 1], cc + 2);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(&bar.tmem_empty[buf], 0));
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // operand preparation
 // ---------------------------------------------------------------------------------------------
 // Power-of-two scaling that puts mx (>= 0) into [2^14, 2^15): returns s = 2^e, inv = 2^-e.
@@ -363,6 +549,16 @@ __global__ void __launch_bounds__(256) transpose_split_upper_f16_kernel(const fl
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// CTA pairs (cta_group::2) for the pre-split rank-k updates?  GQ_GEMM_2CTA=0|1 forces it (read on every call); by default
+// only when there are at least two waves of pair tiles: measured on B200 (profiles/r02/notes.md) the pair kernel gains 2-4 % on
+// the big updates (down_proj, gate/up: 347 / 362 TFLOP/s) and loses as much on the small ones, whose few 256 x 256 tiles leave
+// SM pairs idle in the last wave.
+bool gemm_2cta(int pair_tiles) {
+    const char *e = getenv("GQ_GEMM_2CTA");
+    if (e) return e[0] == '1';
+    return pair_tiles >= 2 * (tc::num_sms() / 2);
+}
+
 template <int BN> int launch(const CUtensorMap &ma, const CUtensorMap &mb, KParams &p, cudaStream_t st) {
     using cfg = Cfg<BN>;
     const int ntm = p.M / BM;
@@ -426,10 +622,11 @@ int gemm_f16x3_nt_presplit(const Split16 &A, const Split16 &B, float *C, long ld
         return GQ_ERR_INVALID;
     }
     const bool wide = N % 256 == 0;
+    const bool pair = wide && M % 256 == 0 && gemm_2cta((M / 256) * (N / 256));      // CTA pairs on 256 x 256 tiles (cta_group::2)
     CUtensorMap ma, mb;
     const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     bool ok = make_map_2d(&ma, (void *)A.data, dt, 2, (uint64_t)A.rows, (uint64_t)A.pitch, 64, BM) &&
-              make_map_2d(&mb, (void *)B.data, dt, 2, (uint64_t)B.rows, (uint64_t)B.pitch, 64, wide ? 256 : 128);
+              make_map_2d(&mb, (void *)B.data, dt, 2, (uint64_t)B.rows, (uint64_t)B.pitch, 64, pair ? 128 : (wide ? 256 : 128));
     if (!ok) {
         gq_set_error("gemm_f16x3_nt_presplit: cuTensorMapEncodeTiled failed");
         return GQ_ERR_CUDA;
@@ -440,6 +637,18 @@ int gemm_f16x3_nt_presplit(const Split16 &A, const Split16 &B, float *C, long ld
     p.C = C; p.ldc = ldc; p.c_batch = 0; p.M = M; p.N = N; p.nkb = K / BK; p.batch = 1;
     p.alpha = alpha; p.beta = beta; p.tile_mode = tg::TM_FULL; p.k_mode = tg::KM_FULL;
     p.sa = A.scale; p.sb = B.scale;
+    if (pair) {
+        // kind::f16 instruction descriptor: D = F32, A/B = F16, both K-major, N = 256, M = 256 (the pair's tile)
+        p.idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        p.ntn = N / 256; p.tiles_per_batch = (M / 256) * p.ntn;
+        GQ_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16x3_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2_BYTES));
+        const int max_pairs = num_sms() / 2;
+        const int pairs = p.tiles_per_batch < max_pairs ? p.tiles_per_batch : max_pairs;
+        gemm_f16x3_2cta_kernel<<<2 * pairs, NTHREADS, SMEM2_BYTES, st>>>(ma, mb, p);
+        gq_count_launches(1);
+        GQ_CHECK_CUDA(cudaGetLastError());
+        return GQ_OK;
+    }
     return wide ? launch<256>(ma, mb, p, st) : launch<128>(ma, mb, p, st);
 }
 

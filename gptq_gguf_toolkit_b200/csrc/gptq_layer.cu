@@ -131,11 +131,11 @@ constexpr int FAST_KMAX = 1024;
 struct FastWs { __half *ut; float *sb; unsigned int *cmax; __half *e16; float *sa; };
 inline size_t al1k(size_t x) { return (x + 1023) / 1024 * 1024; }
 size_t fast_ws_bytes(int d_row, int d_col) {
-    const size_t n = (size_t)d_col, mp = ((size_t)d_row + 127) / 128 * 128;
+    const size_t n = (size_t)d_col, mp = ((size_t)d_row + 255) / 256 * 256;      // rows padded for the CTA-pair tiles
     return 1024 + al1k(4 * n * n) + 2 * al1k(4 * n) + al1k(mp * 2 * FAST_KMAX * 2) + al1k(4 * mp);
 }
 FastWs fast_ws_carve(void *ws, int d_row, int d_col) {
-    const size_t n = (size_t)d_col, mp = ((size_t)d_row + 127) / 128 * 128;
+    const size_t n = (size_t)d_col, mp = ((size_t)d_row + 255) / 256 * 256;
     uint8_t *b = reinterpret_cast<uint8_t *>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
     FastWs w;
     w.ut = (__half *)b; b += al1k(4 * n * n);
@@ -198,7 +198,7 @@ template <int QT> int run_layer(LayerParams p, int mode, void *ws, size_t ws_byt
         gq_set_error("gq_gptq_quantize: fast mode needs %zu workspace bytes", fast_ws_bytes(p.d_row, p.d_col));
         return GQ_ERR_WORKSPACE;
     }
-    const int n = p.d_col, mp = (p.d_row + 127) / 128 * 128, G = fast_group();
+    const int n = p.d_col, mp = (p.d_row + 255) / 256 * 256, G = fast_group();
     const FastWs w = fast_ws_carve(ws, p.d_row, p.d_col);
     {
         ProfScope ps(st, 2);

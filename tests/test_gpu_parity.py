@@ -147,11 +147,12 @@ def test_step_all_zero_weights(ops):
 # GQ_MODE_FAST: rank-k updates between super-blocks on tcgen05 (split-fp16 GEMM, csrc/gemm_f16x3.cu).  Not bit-identical by construction
 # (tensor cores do not reproduce a sequentially rounded fp32 chain): statistical check against exact mode.
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("group", ["1", "2", "4"])
+@pytest.mark.parametrize("group,pair", [("1", "0"), ("2", "0"), ("4", "0"), ("2", "1"), ("4", "1")])
 @pytest.mark.parametrize("shape,tname", [((100, 1024), "Q4_K"), ((256, 1536), "Q6_K"), ((1024, 4096), "Q4_K")])
-def test_fast_mode_statistical(ops, shape, tname, group, monkeypatch):
+def test_fast_mode_statistical(ops, shape, tname, group, pair, monkeypatch):
     from gptq_gguf_toolkit_b200._lib import GQ_MODE_FAST
     monkeypatch.setenv("GQ_FAST_GROUP", group)      # super-blocks per trailing update (read per layer call)
+    monkeypatch.setenv("GQ_GEMM_2CTA", pair)        # one CTA per 128 x 256 tile / CTA pairs on 256 x 256 tiles (cta_group::2)
     d_row, d_col = shape
     torch.manual_seed(d_row + d_col)
     W = (torch.randn(d_row, d_col, device="cuda") * 0.03).contiguous()
