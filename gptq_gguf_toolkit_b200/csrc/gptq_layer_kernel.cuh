@@ -138,7 +138,7 @@ __device__ __noinline__ bool serial_block_impl(Smem &sm, int blk, int warp, int 
             f2_unpack(pr[s >> 1], plo, phi);
             const float x = __shfl_sync(0xffffffffu, (s & 1) ? phi : plo, q, 8);
             const float t = __fadd_rn(x, zz);
-            const float qv = clampf(rintf(SAFE ? ds.div(t) : ds.div_fast(t, bad)), lo, hi);   // :247-254 (kq_quant)
+            const float qv = kq_rint_clamp(SAFE ? ds.div(t) : ds.div_fast(t, bad), lo, hi);   // :247-254 (kq_quant)
             const float wq = kq_dequant(qv, sc, zz);                                          // :255-261
             const float num = __fsub_rn(x, wq);
             const float err = SAFE ? du.div(num) : du.div_fast(num, bad);                     // :264

@@ -22,6 +22,30 @@ template <int GS, class F> __device__ __forceinline__ float kq_sum8(F f) {
     return s;
 }
 
+// clamp(rint(v), lo, hi) without the conversion pipe (FRND issues at a quarter of the FADD rate and has four times its latency, and
+// this sits on the dependent chain of the column steps): t = (v + 1.5*2^23) - 1.5*2^23 is round-to-nearest-even for |v| <= 2^22
+// (the sum lands in [2^23, 2^24], where the spacing is 1 and the magic constant is even, so ties go to the even integer; the
+// subtraction is exact), and for anything larger -- or infinite -- t stays beyond +-2^22 on v's side, so the clamp returns the same
+// bound; NaN stays NaN and leaves fmaxf/fminf as lo either way.  Needs |lo|, |hi| <= 2^22.  The only difference from rintf is the
+// sign of a zero result (+0.0 here where rintf(-0.3f) is -0.0f), which no later operation of the path turns into a different value.
+__device__ __forceinline__ float kq_rint_clamp(float v, float lo, float hi) {
+    const float magic = 12582912.0f;
+    return clampf(__fsub_rn(__fadd_rn(v, magic), magic), lo, hi);
+}
+
+// float((uint8(L) ** 2) mod 256) for an integer-valued L in [0, MAXQ]  (quant_utils.py:246: the codes are uint8, so the square wraps).
+// L*L is exact in fp32; up to MAXQ = 15 it never reaches 256, beyond that 256*floor(L*L/256) is taken off -- the floor by an
+// addition of 2^23 rounded towards zero -- so the sum s_l2 needs no float <-> int conversions.
+template <int MAXQ> __device__ __forceinline__ float kq_sq_u8(float L) {
+    const float l2 = __fmul_rn(L, L);
+    if constexpr (MAXQ * MAXQ < 256) {
+        return l2;
+    } else {
+        const float f = __fsub_rn(__fadd_rz(__fmul_rn(l2, 0.00390625f), 8388608.0f), 8388608.0f);
+        return __fmaf_rn(-256.0f, f, l2);
+    }
+}
+
 // make_k_quants (quant_utils.py:199-274): asymmetric weighted least-squares search for one group.
 // vmask/amask: bit i set when candidate i had D > eps / was accepted (see gq.h search_flags).
 template <int GS, int MAXQ>
@@ -46,7 +70,7 @@ __device__ __forceinline__ void kq_search_asym(const float (&x)[GS], const Searc
     if (isconst) scale = 0.0f;                                                                 // :219
     const float iscale = __frcp_rn(fmaxf(scale, GQ_EPS));                                      // :220
     float best_err = kq_sum8<GS>([&](int k) {                                                  // :223-232
-        float q = clampf(rintf(__fmul_rn(__fsub_rn(x[k], mn), iscale)), 0.0f, fmaxq);
+        float q = kq_rint_clamp(__fmul_rn(__fsub_rn(x[k], mn), iscale), 0.0f, fmaxq);
         if (isconst) q = 0.0f;
         const float diff = __fsub_rn(__fadd_rn(__fmul_rn(scale, q), mn), x[k]);
         return __fmul_rn(w[k], __fmul_rn(diff, diff));
@@ -56,18 +80,13 @@ __device__ __forceinline__ void kq_search_asym(const float (&x)[GS], const Searc
     if (sp.nstep >= 1) {
         for (int i = 0; i <= sp.nstep; ++i) {                                                  // :240
             // :241  python_scalar / tensor == reciprocal(tensor) * fp32(scalar)
-            const float is = __fmul_rn(__frcp_rn(fmaxf(__fsub_rn(mx, xmin), GQ_EPS)), sp.num[i]);
+            // :243  L = 0 for a constant group: all its x equal mn (finite), so a zero inverse scale gives (x - xmin) * 0 = +-0 -> +0
+            const float is = isconst ? 0.0f : __fmul_rn(__frcp_rn(fmaxf(__fsub_rn(mx, xmin), GQ_EPS)), sp.num[i]);
             float L[GS];
 #pragma unroll
-            for (int k = 0; k < GS; ++k) {
-                const float qf = clampf(rintf(__fmul_rn(__fsub_rn(x[k], xmin), is)), 0.0f, fmaxq);  // :242
-                L[k] = isconst ? 0.0f : qf;                                                         // :243
-            }
+            for (int k = 0; k < GS; ++k) L[k] = kq_rint_clamp(__fmul_rn(__fsub_rn(x[k], xmin), is), 0.0f, fmaxq);   // :242
             const float s_l = kq_sum8<GS>([&](int k) { return __fmul_rn(w[k], L[k]); });            // :245
-            const float s_l2 = kq_sum8<GS>([&](int k) {                                             // :246
-                const int l = (int)L[k];
-                return __fmul_rn(w[k], (float)((l * l) & 255));   // uint8 ** 2 wraps mod 256
-            });
+            const float s_l2 = kq_sum8<GS>([&](int k) { return __fmul_rn(w[k], kq_sq_u8<MAXQ>(L[k])); });   // :246  uint8 ** 2 wraps mod 256
             const float s_xl = kq_sum8<GS>([&](int k) { return __fmul_rn(__fmul_rn(w[k], x[k]), L[k]); });  // :247
             const float D = __fsub_rn(__fmul_rn(sum_w, s_l2), __fmul_rn(s_l, s_l));                 // :249
             if (D > GQ_EPS) vmask |= (1u << i);                                                     // :250
@@ -130,14 +149,14 @@ __device__ __forceinline__ void kq_row_finalize(const float *gs, const float *gz
     const float inv_z = mz > 0.0f ? __fmul_rn(__frcp_rn(mz), smq) : 0.0f;                      // :129
 #pragma unroll
     for (int g = 0; g < GPR; ++g) {
-        sq[g] = (uint8_t)(int)clampf(rintf(__fmul_rn(inv_s, gs[g])), 0.0f, smq);               // :132-137
-        zq[g] = (uint8_t)(int)clampf(rintf(__fmul_rn(inv_z, gz[g])), 0.0f, smq);               // :138-143
+        sq[g] = (uint8_t)(int)kq_rint_clamp(__fmul_rn(inv_s, gs[g]), 0.0f, smq);               // :132-137
+        zq[g] = (uint8_t)(int)kq_rint_clamp(__fmul_rn(inv_z, gz[g]), 0.0f, smq);               // :138-143
     }
 }
 
 // quantize / dequantize (quant_utils.py:34-46).  s = d*sq, z = dmin*zq already formed (each one rounding).
 __device__ __forceinline__ float kq_quant(float x, float s, float z, float lo, float hi) {
-    return clampf(rintf(__fdiv_rn(__fadd_rn(x, z), fmaxf(s, GQ_EPS))), lo, hi);
+    return kq_rint_clamp(__fdiv_rn(__fadd_rn(x, z), fmaxf(s, GQ_EPS)), lo, hi);
 }
 __device__ __forceinline__ float kq_dequant(float q, float s, float z) {
     return __fsub_rn(__fmul_rn(s, q), z);

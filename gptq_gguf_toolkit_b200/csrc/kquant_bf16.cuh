@@ -51,7 +51,7 @@ __device__ __forceinline__ void kqb_search_asym(const float (&x)[GS], const Sear
     if (isconst) scale = 0.0f;                                                                  // :219
     const float iscale = rb16(__frcp_rn(fmaxf(scale, eps_t)));                                  // :220
     float best_err = kqb_sum<GS, RND>([&](int k) {                                                   // :223-232
-        float q = clampf(rintf(rb16(__fmul_rn(rb16(__fsub_rn(x[k], mn)), iscale))), 0.0f, fmaxq);
+        float q = kq_rint_clamp(rb16(__fmul_rn(rb16(__fsub_rn(x[k], mn)), iscale)), 0.0f, fmaxq);
         if (isconst) q = 0.0f;
         const float diff = rb16(__fsub_rn(rb16(__fadd_rn(rb16(__fmul_rn(scale, q)), mn)), x[k]));
         return rb16(__fmul_rn(w[k], rb16(__fmul_rn(diff, diff))));
@@ -61,18 +61,13 @@ __device__ __forceinline__ void kqb_search_asym(const float (&x)[GS], const Sear
     if (sp.nstep >= 1) {
         for (int i = 0; i <= sp.nstep; ++i) {                                                   // :240
             // :241  python_scalar / bf16 tensor == round(round(reciprocal(tensor)) * fp32(scalar))
-            const float is = rb16(__fmul_rn(rb16(__frcp_rn(fmaxf(rb16(__fsub_rn(mx, xmin)), eps_t))), sp.num[i]));
+            // (:243  L = 0 for a constant group through a zero inverse scale, as in kquant.cuh)
+            const float is = isconst ? 0.0f : rb16(__fmul_rn(rb16(__frcp_rn(fmaxf(rb16(__fsub_rn(mx, xmin)), eps_t))), sp.num[i]));
             float L[GS];
 #pragma unroll
-            for (int k = 0; k < GS; ++k) {
-                const float qf = clampf(rintf(rb16(__fmul_rn(rb16(__fsub_rn(x[k], xmin)), is))), 0.0f, fmaxq);  // :242
-                L[k] = isconst ? 0.0f : qf;                                                                       // :243
-            }
+            for (int k = 0; k < GS; ++k) L[k] = kq_rint_clamp(rb16(__fmul_rn(rb16(__fsub_rn(x[k], xmin)), is)), 0.0f, fmaxq);   // :242
             const float s_l = kqb_sum<GS, RND>([&](int k) { return rb16(__fmul_rn(w[k], L[k])); });                  // :245
-            const float s_l2 = kqb_sum<GS, RND>([&](int k) {                                                           // :246
-                const int l = (int)L[k];
-                return rb16(__fmul_rn(w[k], (float)((l * l) & 255)));      // uint8 ** 2 wraps mod 256
-            });
+            const float s_l2 = kqb_sum<GS, RND>([&](int k) { return rb16(__fmul_rn(w[k], kq_sq_u8<MAXQ>(L[k]))); });   // :246  uint8 ** 2 wraps mod 256
             const float s_xl = kqb_sum<GS, RND>([&](int k) { return rb16(__fmul_rn(rb16(__fmul_rn(w[k], x[k])), L[k])); });   // :247
             const float D = rb16(__fsub_rn(rb16(__fmul_rn(sum_w, s_l2)), rb16(__fmul_rn(s_l, s_l))));                  // :249
             // (no whole-call skip of a candidate, like the fp32 search: see gq.h search_flags)
@@ -124,8 +119,8 @@ __device__ __forceinline__ void kqb_row_finalize(const float *gs, const float *g
     const float inv_z = mz > 0.0f ? rb16(__fmul_rn(rb16(__frcp_rn(mz)), smq)) : 0.0f;             // :129
 #pragma unroll
     for (int g = 0; g < GPR; ++g) {
-        sq[g] = (uint8_t)(int)clampf(rintf(rb16(__fmul_rn(inv_s, gs[g]))), 0.0f, smq);            // :132-137
-        zq[g] = (uint8_t)(int)clampf(rintf(rb16(__fmul_rn(inv_z, gz[g]))), 0.0f, smq);            // :138-143
+        sq[g] = (uint8_t)(int)kq_rint_clamp(rb16(__fmul_rn(inv_s, gs[g])), 0.0f, smq);            // :132-137
+        zq[g] = (uint8_t)(int)kq_rint_clamp(rb16(__fmul_rn(inv_z, gz[g])), 0.0f, smq);            // :138-143
     }
 }
 

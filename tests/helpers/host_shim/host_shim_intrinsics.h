@@ -20,6 +20,15 @@ static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
+static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+// a + b rounded towards zero: the sum of two floats is exact in double whenever their exponents are less than ~29 apart (all
+// uses: a small non-negative value plus 2^23); the double is then truncated to float
+static inline float __fadd_rz(float a, float b) {
+    const double d = (double)a + (double)b;
+    float r = (float)d;
+    if (std::fabs((double)r) > std::fabs(d)) r = std::nextafterf(r, 0.0f);
+    return r;
+}
 static inline float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
 struct __nv_bfloat16 { uint16_t bits; };

@@ -52,3 +52,39 @@ extern "C" int host_rtn(int qtype, const float *W, int d_row, int d_col, double 
     }
     return -1;
 }
+
+// ---- direct checks of the conversion-free primitives (tests/test_kquant_source_cpu.py) ----
+// kq_rint_clamp(v, lo, hi) against clampf(rintf(v), lo, hi) on a caller-supplied array of raw float bit patterns; returns the
+// number of inputs whose results differ as VALUES (+0.0 == -0.0; NaN results cannot occur: the clamp maps NaN to lo in both).
+extern "C" long host_check_rint_clamp(const uint32_t *bits, long n, float lo, float hi) {
+    long bad = 0;
+    for (long i = 0; i < n; ++i) {
+        float v;
+        std::memcpy(&v, &bits[i], 4);
+        const float a = kq_rint_clamp(v, lo, hi), b = clampf(rintf(v), lo, hi);
+        if (!(a == b)) ++bad;
+    }
+    return bad;
+}
+// the same for EVERY bit pattern in [first, last], both signs
+extern "C" long host_check_rint_clamp_range(uint32_t first, uint32_t last, float lo, float hi) {
+    long bad = 0;
+    for (uint64_t u = first; u <= last; ++u)
+        for (uint32_t sign = 0; sign < 2; ++sign) {
+            const uint32_t b32 = (uint32_t)u | (sign << 31);
+            float v;
+            std::memcpy(&v, &b32, 4);
+            const float a = kq_rint_clamp(v, lo, hi), b = clampf(rintf(v), lo, hi);
+            if (!(a == b)) ++bad;
+        }
+    return bad;
+}
+// kq_sq_u8<MAXQ>(L) against float((uint8(L) ** 2) mod 256) for every integer L in [0, MAXQ]
+extern "C" int host_check_sq_u8() {
+    int bad = 0;
+    for (int l = 0; l <= 3; ++l) bad += kq_sq_u8<3>((float)l) != (float)((l * l) & 255);
+    for (int l = 0; l <= 15; ++l) bad += kq_sq_u8<15>((float)l) != (float)((l * l) & 255);
+    for (int l = 0; l <= 31; ++l) bad += kq_sq_u8<31>((float)l) != (float)((l * l) & 255);
+    for (int l = 0; l <= 255; ++l) bad += kq_sq_u8<255>((float)l) != (float)((l * l) & 255);
+    return bad;
+}

@@ -9,7 +9,6 @@
 #include <map>
 #include <utility>
 
-static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 static inline uint32_t __float_as_uint(float x) { uint32_t u; std::memcpy(&u, &x, 4); return u; }
 static inline float __uint_as_float(uint32_t u) { float x; std::memcpy(&x, &u, 4); return x; }
 static inline long long clock64() { return 0; }

@@ -6,7 +6,6 @@
 #undef __shared__
 #define __shared__ static          // this kernel only has statically sized shared arrays; blocks run one after the other
 #include "host_shim_intrinsics.h"
-static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 #include "sgemm.cuh"
 
 // H <- beta * H + alpha * X^T X  exactly as gq_hessian_update sets it up (csrc/linalg.cu): upper tiles + mirrored store

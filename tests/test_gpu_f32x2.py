@@ -24,6 +24,8 @@ def lib():
     lib.gq_debug_divby.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]
     lib.gq_debug_mulsub2.restype = C.c_int
     lib.gq_debug_mulsub2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]
+    lib.gq_debug_rint_clamp.restype = C.c_int
+    lib.gq_debug_rint_clamp.argtypes = [C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -80,3 +82,15 @@ def test_packed_mul_sub_is_not_contracted(lib):
     assert lib.gq_debug_mulsub2(ta.data_ptr(), te.data_ptr(), tu.data_ptr(), out.data_ptr(), n,
                                 torch.cuda.current_stream().cuda_stream) == 0
     assert np.array_equal(_bits(out.cpu().numpy()), _bits(want))
+
+
+def test_conversion_free_rint_clamp_equals_rintf_on_every_float(lib):
+    """kq_rint_clamp (two FADDs with 1.5 * 2^23 instead of FRND) and kq_sq_u8 (the uint8 square without F2I / I2F) replace rintf and
+    the integer square in the scale search and the column steps: checked on the device for ALL 2^32 bit patterns (NaNs skipped) and
+    the clamp ranges of the five formats and of the scale codes."""
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for lo, hi in ((0.0, 3.0), (0.0, 15.0), (0.0, 31.0), (0.0, 63.0), (-4.0, 3.0), (-32.0, 31.0)):
+        assert lib.gq_debug_rint_clamp(0, 0x7FFFFFFF, lo, hi, bad.data_ptr(), st) == 0
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0

@@ -92,3 +92,29 @@ def test_device_source_matches_oracle_and_packs_like_the_reference(host_lib, gol
     cd = np.uint8 if tname in ("Q2_K", "Q4_K", "Q5_K") else np.int8
     assert np.array_equal(orc.pack(TYPES[tname], five[0].view(cd), five[1].view(np.float16), five[2].view(cd), five[3].view(np.float16),
                                    five[4].view(cd)), g[f"{tname}_ieee_packed"])
+
+
+def test_conversion_free_rint_and_square_equal_the_plain_forms(host_lib):
+    """kq_rint_clamp / kq_sq_u8 (kquant.cuh) replaced rintf and the uint8 square's int conversions in the search and the column steps:
+    same values as clamp(rintf(v)) for EVERY float with 2^-3 <= |v| <= 64 (all bit patterns: ties, half-integers), for zeros,
+    denormals, large / infinite inputs and around the 2^22 / 2^23 / 2^24 boundaries (an exhaustive run over all 2^32 bit patterns
+    found no non-NaN difference; NaNs are left out: on the GPU fmaxf(NaN, lo) is lo in both forms, the host's inlined fmaxf is not
+    IEEE for signalling NaNs); the wrapped square for every code."""
+    lib = host_lib
+    lib.host_check_rint_clamp.restype = C.c_long
+    lib.host_check_rint_clamp.argtypes = [C.POINTER(C.c_uint32), C.c_long, C.c_float, C.c_float]
+    lib.host_check_rint_clamp_range.restype = C.c_long
+    lib.host_check_rint_clamp_range.argtypes = [C.c_uint32, C.c_uint32, C.c_float, C.c_float]
+    special = np.array([0, 1, 2, 0x007FFFFF, 0x00800000, 0x7F800000, 0x7F7FFFFF], dtype=np.uint32)
+    edges = np.concatenate([np.float32(2.0 ** e).view(np.uint32) + np.arange(-64, 65, dtype=np.int64) for e in (21, 22, 23, 24, 25, 31, 60)]).astype(np.uint32)
+    rng = np.random.default_rng(0)
+    rand = rng.integers(0, 2 ** 32, size=1_000_000, dtype=np.uint64).astype(np.uint32)
+    allbits = np.concatenate([special, special | np.uint32(0x80000000), edges, edges | np.uint32(0x80000000), rand])
+    allbits = np.ascontiguousarray(allbits[(allbits & np.uint32(0x7FFFFFFF)) <= np.uint32(0x7F800000)])
+    first, last = int(np.float32(0.125).view(np.uint32)), int(np.float32(64.0).view(np.uint32))
+    for lo, hi in ((0.0, 3.0), (0.0, 15.0), (0.0, 31.0), (0.0, 63.0), (-4.0, 3.0), (-32.0, 31.0)):
+        bad = lib.host_check_rint_clamp(allbits.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_long(allbits.size), C.c_float(lo), C.c_float(hi))
+        assert bad == 0, (lo, hi, bad)
+    for lo, hi in ((0.0, 15.0), (-32.0, 31.0)):
+        assert lib.host_check_rint_clamp_range(C.c_uint32(first), C.c_uint32(last), C.c_float(lo), C.c_float(hi)) == 0
+    assert lib.host_check_sq_u8() == 0
