@@ -195,36 +195,87 @@ def cpu_reference_sample(w, threads: int):
     step = sum(r * t_row[c] for _, r, c in shapes) * nblk
     detail["step_s_per_row"] = {str(k): round(v, 5) for k, v in t_row.items()}
     sample_s["step"] = round(sum(t_row[c] * detail["step_slab_rows"][str(c)] for c in dcols), 2)
-    total = hess + prep + step
-    detail.update(hessian_s=round(hess, 1), prepare_s_total=round(prep, 1), step_s=round(step, 1), sample_seconds=sample_s)
+    # 4. the two forward passes per block the reference driver runs on its device (quantizer.py:150-151, 161-172; here: the CPU), one
+    #    sequence per forward, in the model's dtype: ONE decoder block of the workload's shape on a piece of a sequence, scaled
+    #    linearly to 2 passes x n_seq sequences x all blocks (the attention's quadratic term is under-counted: kinder to the CPU)
+    t_f, L_f = None, min(L, 512)
+    try:
+        from transformers import LlamaConfig, LlamaModel
+        cfg = LlamaConfig(**{k: w[k] for k in ("hidden_size", "intermediate_size", "num_attention_heads", "num_key_value_heads",
+                                               "max_position_embeddings")}, num_hidden_layers=1, vocab_size=1024)
+        old = torch.get_default_dtype()
+        torch.set_default_dtype(getattr(torch, w["dtype"]))
+        try:
+            blk = LlamaModel(cfg).eval()
+        finally:
+            torch.set_default_dtype(old)
+        ids = torch.randint(0, 1024, (1, L_f), generator=g)
+        with torch.no_grad():
+            blk(input_ids=ids)
+            t0 = time.perf_counter()
+            blk(input_ids=ids)
+            t_f = time.perf_counter() - t0
+        del blk
+    except Exception as ex:  # noqa: BLE001
+        detail["forward_sample_failed"] = f"{type(ex).__name__}: {str(ex)[:120]}"
+    fwd = (t_f or 0.0) * (L / L_f) * nseq * 2 * nblk
+    detail["forward_s_per_block_and_piece"] = {"tokens": L_f, "seconds": round(t_f, 4) if t_f else None, "dtype": w["dtype"]}
+    sample_s["forwards"] = round(2 * (t_f or 0.0), 2)
+    # 5. embed_tokens / lm_head round-to-nearest (quantizer.py:278-330): rows are independent, a 1024-row slab of each
+    t0 = time.perf_counter()
+    orc.rtn_quantize((np.random.default_rng(7).standard_normal((1024, w["hidden_size"])) * 0.02).astype(np.float32), 12)
+    t_r = time.perf_counter() - t0
+    rtn = t_r * (2 * w["vocab_size"] / 1024)
+    sample_s["rtn"] = round(t_r, 2)
+    hot = hess + prep + step
+    total = hot + fwd + rtn
+    detail.update(hessian_s=round(hess, 1), prepare_s_total=round(prep, 1), step_s=round(step, 1), forwards_s=round(fwd, 1), rtn_s=round(rtn, 1),
+                  hot_path_only_s=round(hot, 1), sample_seconds=sample_s, sample_total_s=round(sum(sample_s.values()), 2))
     return total, detail
 
 
 CPU_SAMPLE_NOTE = ("per phase: H.addmm_ of 16 sequences of 2048 tokens at each d_col, one Cholesky chain (cholesky, cholesky_inverse, "
-                   "cholesky upper) at each d_col, the column loop on whole-width slabs (2048 rows x 4096, 512 rows x 14336); scaled by "
-                   "algorithmic work to 32 blocks x 7 projections x 128 sequences -- EXTRAPOLATED, hot path only (no model forwards, "
-                   "no embed/lm_head), oracle PORT of the reference (see reference_measured for the reference's own functions)")
+                   "cholesky upper) at each d_col, the column loop on whole-width slabs (2048 rows x 4096, 512 rows x 14336), one decoder "
+                   "block forward on 512 tokens in the model dtype, RTN of a 1024-row slab; each scaled by its algorithmic work to the whole "
+                   "job (32 blocks x 7 projections x 128 sequences, 2 forward passes per block, embed_tokens + lm_head) -- EXTRAPOLATED; "
+                   "detail.hot_path_only_s is the hot path alone (Hessian + Cholesky chain + column loop); oracle PORT of the reference "
+                   "(see reference_measured for the reference's own functions)")
+
+
+def bench_config(args, w, world, qdesc, main_mode):
+    """The `config` object of the JSON line -- the SAME for both arms (the reference arm runs the workload the own arm names)."""
+    return {"workload": f"{args.workload}: random-init {w['dtype']} Llama ({w['num_hidden_layers']} blocks, d_model {w['hidden_size']}), "
+                        f"{w['n_seq']} calib seqs x {w['seq_len']}, {qdesc}, {main_mode} mode",
+            "calibration_batch": args.batch, "l2": "inputs (16 GB weights + 2 GB activations) exceed the 126 MB L2; no flush needed",
+            "parallelism": f"dp{world} over calibration sequences + row-sharded quantisation" if world > 1 else "single GPU"}
 
 
 def run_reference_arm(args, w):
+    """`value` = the metric (seconds for the whole job) EXTRAPOLATED from the bounded sample; `ms_per_step` = the time one timed
+    step (one sample) really took, so that steps x ms_per_step is the run's own duration."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     for _ in range(max(0, args.warmup - 2)):      # the sample is deterministic CPU work; one warm-up is plenty
         cpu_reference_sample(w, threads)
-    vals, detail = [], None
+    vals, walls, detail = [], [], None
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         v, detail = cpu_reference_sample(w, threads)
+        walls.append(time.perf_counter() - t0)
         vals.append(v)
     v = sum(vals) / len(vals)
-    sample = CPU_SAMPLE_NOTE
+    main_mode = "fast" if args.mode == "fast" else "exact"
+    qdesc = f"uniform {args.qtype}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(walls) / len(walls), "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload + " uniform Q4_K, CPU oracle port, extrapolated from a bounded sample", **{k: w[k] for k in ("n_seq", "seq_len")}},
-        "cpu_baseline": {"value": v, "unit": "s", "cores": threads, "kind": "port", "sample": sample, "extrapolated": True,
+        "config": bench_config(args, w, args.gpus, qdesc, main_mode),
+        "value_note": "whole-job seconds EXTRAPOLATED from the bounded CPU sample each step times (ms_per_step is the sample's own wall "
+                      "time); runs on rank 0's host cores only, whatever --gpus says",
+        "cpu_baseline": {"value": v, "unit": "s", "cores": threads, "kind": "port", "sample": CPU_SAMPLE_NOTE, "extrapolated": True,
                          "sample_seconds": detail.get("sample_seconds"), "detail": detail, "reference_measured": REFERENCE_MEASURED},
         "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -571,10 +622,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: random-init {w['dtype']} Llama ({w['num_hidden_layers']} blocks, d_model {w['hidden_size']}), "
-                                   f"{w['n_seq']} calib seqs x {w['seq_len']}, {qdesc}, {main_mode} mode",
-                       "calibration_batch": args.batch, "l2": "inputs (16 GB weights + 2 GB activations) exceed the 126 MB L2; no flush needed",
-                       "parallelism": f"dp{world} over calibration sequences + row-sharded quantisation" if world > 1 else "single GPU"},
+            "config": bench_config(args, w, world, qdesc, main_mode),
             "roofline": roofline,
             "phases_s": {k: round(v, 4) for k, v in sorted(phases.items())},
             "hot_path_s": round(hot, 4),

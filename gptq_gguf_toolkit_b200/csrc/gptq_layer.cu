@@ -33,7 +33,7 @@ using rk::ES_FLOATS;
 
 template <int QT> int launch_layer(const LayerParams &p, cudaStream_t st) {
     const int grid = (p.d_row + R - 1) / R;
-    const size_t smem = p.perm == nullptr ? SMEM_NO_PERM : sizeof(Smem);
+    const size_t smem = sizeof(Smem);
     GQ_CHECK_CUDA(cudaFuncSetAttribute(gptq_layer_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
     gptq_layer_kernel<QT><<<grid, NT, smem, st>>>(p);
     gq_count_launches(1);

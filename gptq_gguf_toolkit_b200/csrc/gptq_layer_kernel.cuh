@@ -67,12 +67,14 @@ struct __align__(16) Smem {
     float dummy_f[64];                       // sink of the non-owner lanes' stores in the serial phase
     uint8_t dummy_b[32];
     RowScales<R> rs;
-    // act_order only -- kept LAST: launches without a permutation allocate the struct up to here (SMEM_NO_PERM)
-    float pc_sc[R * 128];                    // per (row, column of the block) scale, zero, checked 1/scale
-    float pc_zz[R * 128];
-    float pc_y[R * 128];
+    union {
+        // act_order only: per (row, column of the block) scale, zero, checked 1/scale
+        struct { float pc_sc[R * 128]; float pc_zz[R * 128]; float pc_y[R * 128]; };
+        // without a permutation: the off-diagonal block U[c:c+128, c+128:c+256] of the in-super-block update, prefetched underneath
+        // the scale search (mid_update_smem)
+        float Uoff[128 * 128];
+    };
 };
-constexpr size_t SMEM_NO_PERM = offsetof(Smem, pc_sc);
 
 // Shared-memory layout of the (128 x 128) diagonal block of U for the serial phase: in row i the 16 values a
 // lane (l8 = j & 7) needs -- columns j = 8s + l8 -- are contiguous (64 B), 16-byte chunks XOR-swizzled by (l8 >> 1) & 3
@@ -172,6 +174,48 @@ __device__ __forceinline__ void serial_block(Smem &sm, int blk, int warp, int la
     for (int s = 0; s < 16; ++s) sm.Wt[wt_idx(srow, blk * 128 + 8 * s + l8)] = sm.Wq[srow * 128 + 8 * s + l8];
 }
 
+// The in-super-block update  tile[:, 128:256] -= E_0 (32 x 128) * U[c:c+128, c+128:c+256]  (gptq.py:270 for the super-block's first
+// 128-column block) with BOTH operands already in shared memory: the errors are the serial phase's own output (Et), the block of U
+// was prefetched underneath the scale search (Uoff).  All 8 warps take part -- warp w owns rows 4w..4w+3, lane l the columns
+// 128 + 4l .. 128 + 4l + 3 -- where the streaming rank_update<true> kept only the four ch == 1 warps (two of the four SM
+// sub-partitions) busy and paid eight pipeline barriers.  Same arithmetic per element: one fresh single-accumulator FMA chain over
+// the 128 k's in ascending order, then one subtraction.
+__device__ __forceinline__ void mid_update_smem(Smem &sm, int warp, int lane) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    const float *ub = sm.Uoff + 4 * lane;
+    const float *eb = sm.Et + (4 * warp) * 128;
+#pragma unroll 2
+    for (int kk = 0; kk < 128; kk += 4) {
+        float4 e[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e[i] = *reinterpret_cast<const float4 *>(eb + i * 128 + kk);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+            const float4 u = *reinterpret_cast<const float4 *>(ub + (kk + k2) * 128);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float ev = k2 == 0 ? e[i].x : k2 == 1 ? e[i].y : k2 == 2 ? e[i].z : e[i].w;
+                acc[i][0] = __fmaf_rn(ev, u.x, acc[i][0]);
+                acc[i][1] = __fmaf_rn(ev, u.y, acc[i][1]);
+                acc[i][2] = __fmaf_rn(ev, u.z, acc[i][2]);
+                acc[i][3] = __fmaf_rn(ev, u.w, acc[i][3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float4 *wp = reinterpret_cast<float4 *>(sm.Wt + wt_idx4(4 * warp + i, 32 + lane));
+        float4 v = *wp;
+        v.x = __fsub_rn(v.x, acc[i][0]); v.y = __fsub_rn(v.y, acc[i][1]);
+        v.z = __fsub_rn(v.z, acc[i][2]); v.w = __fsub_rn(v.w, acc[i][3]);
+        *wp = v;
+    }
+}
+
 // (A register-capped build of this kernel for the panel launches of the right-looking schedule -- __launch_bounds__(256, 2),
 // 128 registers, two co-resident CTAs per SM -- was measured on B200 and was 3-5 % SLOWER at every shape: the K-quant search
 // of the 32-weight-group types spills, and the column steps lose the registers that keep their loads ahead of the chain.)
@@ -193,6 +237,14 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
         for (int id = tid; id < 128 * 128; id += NT) {
             const int i = id >> 7, j = id & 127;
             if (j >= (i & ~31)) cp_async4(sm.u.Ud + ud_idx(i, j), p.U + (size_t)(c1 + i) * ld + c1 + j);
+        }
+        cp_async_commit();
+    };
+    auto load_Uoff = [&](int c1) {   // U[c1:c1+128, c1+128:c1+256] -> Uoff (row-major), 16 x 16-byte cp.async per thread
+#pragma unroll 4
+        for (int id = tid; id < 128 * 32; id += NT) {
+            const int i = id >> 5, c4 = id & 31;
+            cp_async16(sm.Uoff + i * 128 + 4 * c4, p.U + (size_t)(c1 + i) * ld + c1 + 128 + 4 * c4);
         }
         cp_async_commit();
     };
@@ -260,6 +312,7 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
         // scale / min search on the live tile (gptq.py:240-245 -> quant_utils.py:90-145); U's diagonal
         // block for the first 128 columns streams in underneath it.
         load_Ud(c);
+        if (!per_col) load_Uoff(c);
         if (!p.static_scales) {
             uint32_t vmask = 0, amask = 0;
             tile_search<QT, R, NT>(sm.Wt, sm.gsc, sm.gzr, p.sp, vmask, amask);
@@ -303,24 +356,31 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
         __syncthreads();
         pc.lap(PH_SERIAL0);
         store_E(c);
-        __syncthreads();   // E of block 0 visible to the whole CTA; Ud is free again
 
         // the first block's rank-k update onto the super-block's second half
-        if (ch == 1) {
+        if (!per_col) {
+            // Ud is free (every warp is past serial_block 0): the next diagonal block streams in underneath the update, whose
+            // operands are both in shared memory already
+            load_Ud(c + 128);
+            mid_update_smem(sm, warp, lane);
+        } else {
+            __syncthreads();   // E of block 0 visible (global) to the whole CTA
+            if (ch == 1) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 v = *reinterpret_cast<const float4 *>(sm.Wt + wt_idx4(8 * rg + i, 32 + lane));
-                w[i][0] = v.x; w[i][1] = v.y; w[i][2] = v.z; w[i][3] = v.w;
+                for (int i = 0; i < 8; ++i) {
+                    const float4 v = *reinterpret_cast<const float4 *>(sm.Wt + wt_idx4(8 * rg + i, 32 + lane));
+                    w[i][0] = v.x; w[i][1] = v.y; w[i][2] = v.z; w[i][3] = v.w;
+                }
             }
-        }
-        rank_update<true>(w, p, sm.u.pipe.Us, sm.u.pipe.Es, r0, c, c, c + 128, tid, rg, ch, lane);
-        if (ch == 1) {
+            rank_update<true>(w, p, sm.u.pipe.Us, sm.u.pipe.Es, r0, c, c, c + 128, tid, rg, ch, lane);
+            if (ch == 1) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                *reinterpret_cast<float4 *>(sm.Wt + wt_idx4(8 * rg + i, 32 + lane)) =
-                    make_float4(w[i][0], w[i][1], w[i][2], w[i][3]);
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<float4 *>(sm.Wt + wt_idx4(8 * rg + i, 32 + lane)) =
+                        make_float4(w[i][0], w[i][1], w[i][2], w[i][3]);
+            }
+            load_Ud(c + 128);
         }
-        load_Ud(c + 128);
         cp_async_wait<0>();
         __syncthreads();
         diag_recip();

@@ -89,7 +89,7 @@ def main():
             fl = rows * n * (n - 128)
             print(f"gptq {rows}x{n}: {mn:.2f} ms -> rank-k {fl / mn / 1e9:.1f} TFLOP/s", flush=True)
             phase_clocks(lambda: ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16), (rows + 31) // 32)
-            for grp in ("1", "2", "4"):
+            for grp in (() if "nofast" in what else ("1", "2", "4")):
                 os.environ["GQ_FAST_GROUP"] = grp
                 mn, av = timed(lambda: ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16, mode=1), warm=1, it=2)
                 ops.profile_enable(True)
