@@ -64,8 +64,6 @@ struct __align__(16) Smem {
     float gzr[R * 16];
     float dg_b[128];                         // diagonal of the current U block and its checked reciprocal (DivBy)
     float dg_y[128];
-    float dummy_f[64];                       // sink of the non-owner lanes' stores in the serial phase
-    uint8_t dummy_b[32];
     RowScales<R> rs;
     union {
         // act_order only: per (row, column of the block) scale, zero, checked 1/scale
@@ -76,19 +74,16 @@ struct __align__(16) Smem {
     };
 };
 
-// Shared-memory layout of the (128 x 128) diagonal block of U for the serial phase: in row i the 16 values a
-// lane (l8 = j & 7) needs -- columns j = 8s + l8 -- are contiguous (64 B), 16-byte chunks XOR-swizzled by (l8 >> 1) & 3
-// so that the eight lanes of a row group read eight different bank groups with one LDS.128 each.
-__device__ __forceinline__ int ud_idx(int i, int j) {
-    const int l8 = j & 7, sgrp = j >> 3;
-    return i * 128 + l8 * 16 + ((((sgrp >> 2) ^ (l8 >> 1)) & 3) << 2) + (sgrp & 3);
-}
-
-// The 128 sequential column steps of one block (gptq.py:229-268), all 8 warps (two per SM sub-partition, so that
-// one warp's off-chain work fills the other's dependency stalls).  8 lanes per row; lane l8 holds the block's columns
-// {8s + l8}, s = 0..15, as 8 packed pairs.  Column i = 8s+q is broadcast from its owner, every lane of the row redoes
-// the (cheap) quantise/err arithmetic, then updates its not-yet-consumed columns:  w -= fl(err * U[i, j])
-// (two roundings: f2_mul_nofuse then sub.rn.f32x2).
+// The 128 sequential column steps of one block (gptq.py:229-268), all 8 warps (two per SM sub-partition, so that one warp's
+// off-chain work fills the other's dependency stalls).  8 lanes per row.  Lane l8 holds the block's columns in groups of four:
+// slot m (0..3) = columns 32m + 4*l8 .. +3, as two packed pairs -- so the diagonal block of U sits in shared memory in plain
+// row-major order (16-byte cp.async, and a lane's part of row i is one LDS.128 per slot; the eight lanes of a row read 128
+// contiguous bytes).  The columns are consumed in order i = 32m + 4q + p (slot m, owner lane q, position p): at the start of a
+// group every lane fetches the owner's four values (four shuffles, once per four columns) and then carries that group REDUNDANTLY
+// through its four steps -- quantise, error, w[j] -= fl(err * U[i, j]) on the group's remaining columns -- so the dependent chain
+// of a column step holds no shuffle at all: 16 fp32 operations.  Every lane also updates its own not-yet-consumed slots
+// (two roundings per element: f2_mul_nofuse then sub.rn.f32x2; the already consumed columns of the slots it touches see U's
+// zeros below the diagonal).
 // The two divisions of the dependent chain -- (x + z) / max(s, eps) and (x - w_q) / U[i,i] -- use reciprocals prepared
 // off the chain (DivBy, f32x2.cuh).  SAFE = false: branch-free (DivBy::div_fast, stores through a select-ed pointer);
 // returns true if some quotient was outside the range in which div_fast is proven exact -- the caller then reruns the
@@ -97,67 +92,94 @@ __device__ __forceinline__ int ud_idx(int i, int j) {
 template <int QT, bool SAFE>
 __device__ __noinline__ bool serial_block_impl(Smem &sm, int blk, int warp, int lane, f2_t nz2, bool per_col) {
     constexpr int GS = Fmt<QT>::GS;
+    constexpr int NH = 32 / GS;              // scale groups per 32-column span (1 or 2)
     const float lo = (float)Fmt<QT>::QMIN, hi = (float)Fmt<QT>::QMAX;
     const int l8 = lane & 7, srow = warp * 4 + (lane >> 3);
     f2_t pr[8];
 #pragma unroll
-    for (int m = 0; m < 8; ++m)
-        pr[m] = f2_pack(sm.Wt[wt_idx(srow, blk * 128 + 16 * m + l8)], sm.Wt[wt_idx(srow, blk * 128 + 16 * m + 8 + l8)]);
+    for (int m = 0; m < 4; ++m) {
+        const float4 v = *reinterpret_cast<const float4 *>(sm.Wt + wt_idx4(srow, blk * 32 + 8 * m + l8));
+        pr[2 * m] = f2_pack(v.x, v.y);
+        pr[2 * m + 1] = f2_pack(v.z, v.w);
+    }
     const float d = sm.rs.d[srow], dm = sm.rs.dm[srow];
-    const float *Ud = sm.u.Ud + l8 * 16;
-    const int sw = (l8 >> 1) & 3;
+    const float *Ud = sm.u.Ud + 4 * l8;
     float *et = sm.Et + srow * 128, *wqo = sm.Wq + srow * 128;
     uint8_t *cd = sm.codes + srow * 256 + blk * 128;
     float sc = 0.0f, zz = 0.0f;
     DivBy ds = DivBy::make(1.0f);
     bool bad = false;
 #pragma unroll
-    for (int s = 0; s < 16; ++s) {
-        if (!per_col && (8 * s) % GS == 0) {
-            const int g = (blk * 128 + 8 * s) / GS;
-            sc = __fmul_rn(d, kq_code_to_f<QT>(sm.rs.sq[srow][g]));
-            zz = __fmul_rn(dm, kq_code_to_f<QT>(sm.rs.zq[srow][g]));
-            ds = DivBy::make(fmaxf(sc, GQ_EPS));
-        }
+    for (int m = 0; m < 4; ++m) {
 #pragma unroll 1
-        for (int q = 0; q < 8; ++q) {
-            const int i = 8 * s + q;
-            // loads that do not depend on the chain first: U[i, my columns], the diagonal's reciprocal
-            const float4 *urow = reinterpret_cast<const float4 *>(Ud + i * 128);
-            float4 u[4];
-#pragma unroll
-            for (int c4 = s >> 2; c4 < 4; ++c4) u[c4] = urow[c4 ^ sw];
-            DivBy du;
-            du.b = sm.dg_b[i];
-            du.y = sm.dg_y[i];
-            if (per_col) {          // act_order: every column has its own group (gptq.py:233-238)
-                sc = sm.pc_sc[srow * 128 + i];
-                zz = sm.pc_zz[srow * 128 + i];
-                ds.b = fmaxf(sc, GQ_EPS);
-                ds.y = sm.pc_y[srow * 128 + i];
+        for (int h = 0; h < NH; ++h) {
+            if (!per_col) {
+                const int g = (blk * 128 + 32 * m) / GS + h;
+                sc = __fmul_rn(d, kq_code_to_f<QT>(sm.rs.sq[srow][g]));
+                zz = __fmul_rn(dm, kq_code_to_f<QT>(sm.rs.zq[srow][g]));
+                ds = DivBy::make(fmaxf(sc, GQ_EPS));
             }
-            float plo, phi;
-            f2_unpack(pr[s >> 1], plo, phi);
-            const float x = __shfl_sync(0xffffffffu, (s & 1) ? phi : plo, q, 8);
-            const float t = __fadd_rn(x, zz);
-            const float qv = kq_rint_clamp(SAFE ? ds.div(t) : ds.div_fast(t, bad), lo, hi);   // :247-254 (kq_quant)
-            const float wq = kq_dequant(qv, sc, zz);                                          // :255-261
-            const float num = __fsub_rn(x, wq);
-            const float err = SAFE ? du.div(num) : du.div_fast(num, bad);                     // :264
-            const f2_t e2 = f2_pack(err, err);
+#pragma unroll 1
+            for (int q = h * (8 / NH); q < (h + 1) * (8 / NH); ++q) {
+                // the owner's four columns, replicated in every lane of the row
+                float xg[4];
+                {
+                    float a0, a1, a2, a3;
+                    f2_unpack(pr[2 * m], a0, a1);
+                    f2_unpack(pr[2 * m + 1], a2, a3);
+                    xg[0] = __shfl_sync(0xffffffffu, a0, q, 8);
+                    xg[1] = __shfl_sync(0xffffffffu, a1, q, 8);
+                    xg[2] = __shfl_sync(0xffffffffu, a2, q, 8);
+                    xg[3] = __shfl_sync(0xffffffffu, a3, q, 8);
+                }
+                float errs[4], wqs[4];
+                uint32_t code4 = 0;
 #pragma unroll
-            for (int c4 = s >> 2; c4 < 4; ++c4) {                                             // :267
-                if (2 * c4 >= (s >> 1)) pr[2 * c4] = f2_sub(pr[2 * c4], f2_mul_nofuse(e2, f2_pack(u[c4].x, u[c4].y), nz2));
-                pr[2 * c4 + 1] = f2_sub(pr[2 * c4 + 1], f2_mul_nofuse(e2, f2_pack(u[c4].z, u[c4].w), nz2));
+                for (int pp = 0; pp < 4; ++pp) {
+                    const int i = 32 * m + 4 * q + pp;
+                    // loads that do not depend on the chain first: U[i, my columns], U[i, the group's columns], the diagonal's reciprocal
+                    const float *urow = Ud + i * 128;
+                    float4 u[4];
+#pragma unroll
+                    for (int c4 = m; c4 < 4; ++c4) u[c4] = *reinterpret_cast<const float4 *>(urow + 32 * c4);
+                    const float4 ug = *reinterpret_cast<const float4 *>(sm.u.Ud + i * 128 + 32 * m + 4 * q);
+                    DivBy du;
+                    du.b = sm.dg_b[i];
+                    du.y = sm.dg_y[i];
+                    if (per_col) {          // act_order: every column has its own group (gptq.py:233-238)
+                        sc = sm.pc_sc[srow * 128 + i];
+                        zz = sm.pc_zz[srow * 128 + i];
+                        ds.b = fmaxf(sc, GQ_EPS);
+                        ds.y = sm.pc_y[srow * 128 + i];
+                    }
+                    const float x = xg[pp];
+                    const float t = __fadd_rn(x, zz);
+                    const float qv = kq_rint_clamp(SAFE ? ds.div(t) : ds.div_fast(t, bad), lo, hi);   // :247-254 (kq_quant)
+                    const float wq = kq_dequant(qv, sc, zz);                                          // :255-261
+                    const float num = __fsub_rn(x, wq);
+                    const float err = SAFE ? du.div(num) : du.div_fast(num, bad);                     // :264
+                    // the group's remaining columns (the replicated copy): w -= fl(err * u), two roundings     :267
+                    if (pp < 1) xg[1] = __fsub_rn(xg[1], __fmul_rn(err, ug.y));
+                    if (pp < 2) xg[2] = __fsub_rn(xg[2], __fmul_rn(err, ug.z));
+                    if (pp < 3) xg[3] = __fsub_rn(xg[3], __fmul_rn(err, ug.w));
+                    const f2_t e2 = f2_pack(err, err);
+#pragma unroll
+                    for (int c4 = m; c4 < 4; ++c4) {                                                  // :267
+                        pr[2 * c4] = f2_sub(pr[2 * c4], f2_mul_nofuse(e2, f2_pack(u[c4].x, u[c4].y), nz2));
+                        pr[2 * c4 + 1] = f2_sub(pr[2 * c4 + 1], f2_mul_nofuse(e2, f2_pack(u[c4].z, u[c4].w), nz2));
+                    }
+                    errs[pp] = err;                                                                   // :268
+                    wqs[pp] = wq;                                                                     // :266
+                    code4 |= (uint32_t)(uint8_t)(int8_t)(int)qv << (8 * pp);                          // :263
+                }
+                // outputs of the group's four columns (identical in the row's eight lanes): one lane stores them, 16 + 16 + 4 bytes
+                if (l8 == 0) {
+                    const int i0 = 32 * m + 4 * q;
+                    *reinterpret_cast<float4 *>(et + i0) = make_float4(errs[0], errs[1], errs[2], errs[3]);
+                    *reinterpret_cast<float4 *>(wqo + i0) = make_float4(wqs[0], wqs[1], wqs[2], wqs[3]);
+                    *reinterpret_cast<uint32_t *>(cd + i0) = code4;
+                }
             }
-            // outputs of column i: the owner lane stores, the others write to a per-lane dummy slot (no branch)
-            const bool own = (l8 == q);
-            float *ep = own ? et + i : sm.dummy_f + lane;
-            float *wp = own ? wqo + i : sm.dummy_f + 32 + lane;
-            uint8_t *cp = own ? cd + i : sm.dummy_b + lane;
-            *ep = err;                                                                        // :268
-            *wp = wq;                                                                         // :266
-            *cp = (uint8_t)(int8_t)(int)qv;                                                   // :263
         }
     }
     return bad;
@@ -231,14 +253,22 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
     const int nsb = p.d_col / GQ_QK_K, ng = p.d_col / GS;
     const size_t ld = (size_t)p.d_col;
 
-    // Diagonal (128 x 128) block of U -> shared memory in the serial phase's permuted layout (ud_idx).  Row i only
-    // needs its columns j >= 32*(i/32) (the lanes read whole 16-byte chunks = 32-column spans at and right of the diagonal).
+    // Diagonal (128 x 128) block of U -> shared memory, row-major.  Row i only needs its columns j >= 32*(i/32) (the lanes read
+    // whole 32-column spans at and right of the diagonal).
     auto load_Ud = [&](int c1) {
-        for (int id = tid; id < 128 * 128; id += NT) {
-            const int i = id >> 7, j = id & 127;
-            if (j >= (i & ~31)) cp_async4(sm.u.Ud + ud_idx(i, j), p.U + (size_t)(c1 + i) * ld + c1 + j);
+#pragma unroll 4
+        for (int id = tid; id < 128 * 32; id += NT) {
+            const int i = id >> 5, c4 = id & 31;
+            if (4 * c4 >= (i & ~31)) cp_async16(sm.u.Ud + i * 128 + 4 * c4, p.U + (size_t)(c1 + i) * ld + c1 + 4 * c4);
         }
         cp_async_commit();
+    };
+    auto diag_recip = [&]() {      // after Ud has landed: checked reciprocals of the diagonal (off the dependent chain)
+        if (tid < 128) {
+            const DivBy dv = DivBy::make(sm.u.Ud[tid * 128 + tid]);
+            sm.dg_b[tid] = dv.b;
+            sm.dg_y[tid] = dv.y;
+        }
     };
     auto load_Uoff = [&](int c1) {   // U[c1:c1+128, c1+128:c1+256] -> Uoff (row-major), 16 x 16-byte cp.async per thread
 #pragma unroll 4
@@ -247,13 +277,6 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
             cp_async16(sm.Uoff + i * 128 + 4 * c4, p.U + (size_t)(c1 + i) * ld + c1 + 128 + 4 * c4);
         }
         cp_async_commit();
-    };
-    auto diag_recip = [&]() {      // after Ud has landed: checked reciprocals of the diagonal (off the dependent chain)
-        if (tid < 128) {
-            const DivBy dv = DivBy::make(sm.u.Ud[ud_idx(tid, tid)]);
-            sm.dg_b[tid] = dv.b;
-            sm.dg_y[tid] = dv.y;
-        }
     };
     auto store_E = [&](int c1) {   // errors of the block replace the consumed columns of W
 #pragma unroll
