@@ -102,3 +102,28 @@ struct DivBy {
         return a == 0.0f ? q0 : q;
     }
 };
+
+// The same Markstein quotient for the dependent chain of the column steps, with the bookkeeping reduced to integer min / max
+// accumulators (no predicates, no selects):  `ok()` afterwards says whether EVERY dividend seen was zero or inside
+// (2^-60, 2^60) -- u2 = bits(a) << 1 drops the sign; a zero dividend gives u2 - 1 = 0xFFFFFFFF and never lowers the minimum.
+// The divisor's own check (y != 0, DivBy::make) is the caller's, once per divisor instead of once per quotient.
+// For a zero dividend the result is a zero whose SIGN may differ from IEEE's; the callers' next operation is either the magic-number
+// rint of kq_rint_clamp_bits (which returns +0 for both) or a product that is subtracted from a weight (w - (+-0) == w; a zero
+// weight can change its sign, and again meets the rint first), so no output value depends on it.
+struct DivRange {
+    uint32_t hi2 = 0u, lo2m1 = 0xFFFFFFFFu;
+    __device__ __forceinline__ void see(float a) {
+        const uint32_t u2 = __float_as_uint(a) << 1;
+        hi2 = max(hi2, u2);
+        lo2m1 = min(lo2m1, u2 - 1u);
+    }
+    __device__ __forceinline__ bool ok() const {       // all |a| < 2^60 and all non-zero |a| > 2^-60
+        return hi2 < (0x5D800000u << 1) && lo2m1 >= (0x21800000u << 1);
+    }
+};
+__device__ __forceinline__ float div_chain(float a, float b, float y, DivRange &rg) {
+    rg.see(a);
+    const float q0 = __fmul_rn(a, y);
+    const float r = __fmaf_rn(-q0, b, a);
+    return __fmaf_rn(r, y, q0);
+}

@@ -64,6 +64,7 @@ struct __align__(16) Smem {
     float gzr[R * 16];
     float dg_b[128];                         // diagonal of the current U block and its checked reciprocal (DivBy)
     float dg_y[128];
+    int dg_unsafe[4];                        // per warp of diag_recip: some dg_y is 0 (= "use the IEEE division") -> the block takes the SAFE path
     RowScales<R> rs;
     union {
         // act_order only: per (row, column of the block) scale, zero, checked 1/scale
@@ -89,8 +90,8 @@ struct __align__(16) Smem {
 // returns true if some quotient was outside the range in which div_fast is proven exact -- the caller then reruns the
 // block with SAFE = true (IEEE fallback inside DivBy::div).  The block's initial values are read from Wt, its
 // dequantised values go to `Wq` (a separate buffer), so a rerun starts from unchanged inputs.
-template <int QT, bool SAFE>
-__device__ __noinline__ bool serial_block_impl(Smem &sm, int blk, int warp, int lane, f2_t nz2, bool per_col) {
+template <int QT, bool SAFE, bool per_col>
+__device__ __noinline__ bool serial_block_impl(Smem &sm, int blk, int warp, int lane, f2_t nz2) {
     constexpr int GS = Fmt<QT>::GS;
     constexpr int NH = 32 / GS;              // scale groups per 32-column span (1 or 2)
     const float lo = (float)Fmt<QT>::QMIN, hi = (float)Fmt<QT>::QMAX;
@@ -108,7 +109,8 @@ __device__ __noinline__ bool serial_block_impl(Smem &sm, int blk, int warp, int 
     uint8_t *cd = sm.codes + srow * 256 + blk * 128;
     float sc = 0.0f, zz = 0.0f;
     DivBy ds = DivBy::make(1.0f);
-    bool bad = false;
+    bool bad = (sm.dg_unsafe[0] | sm.dg_unsafe[1] | sm.dg_unsafe[2] | sm.dg_unsafe[3]) != 0;   // a diagonal element of U without a checked reciprocal
+    DivRange rng;
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
 #pragma unroll 1
@@ -118,6 +120,7 @@ __device__ __noinline__ bool serial_block_impl(Smem &sm, int blk, int warp, int 
                 sc = __fmul_rn(d, kq_code_to_f<QT>(sm.rs.sq[srow][g]));
                 zz = __fmul_rn(dm, kq_code_to_f<QT>(sm.rs.zq[srow][g]));
                 ds = DivBy::make(fmaxf(sc, GQ_EPS));
+                bad = bad || ds.y == 0.0f;
             }
 #pragma unroll 1
             for (int q = h * (8 / NH); q < (h + 1) * (8 / NH); ++q) {
@@ -132,6 +135,10 @@ __device__ __noinline__ bool serial_block_impl(Smem &sm, int blk, int warp, int 
                     xg[2] = __shfl_sync(0xffffffffu, a2, q, 8);
                     xg[3] = __shfl_sync(0xffffffffu, a3, q, 8);
                 }
+                // the diagonal's checked reciprocals for the group's four columns, ahead of the chain
+                const int i0 = 32 * m + 4 * q;
+                const float4 dgb = *reinterpret_cast<const float4 *>(sm.dg_b + i0);
+                const float4 dgy = *reinterpret_cast<const float4 *>(sm.dg_y + i0);
                 float errs[4], wqs[4];
                 uint32_t code4 = 0;
 #pragma unroll
@@ -144,20 +151,22 @@ __device__ __noinline__ bool serial_block_impl(Smem &sm, int blk, int warp, int 
                     for (int c4 = m; c4 < 4; ++c4) u[c4] = *reinterpret_cast<const float4 *>(urow + 32 * c4);
                     const float4 ug = *reinterpret_cast<const float4 *>(sm.u.Ud + i * 128 + 32 * m + 4 * q);
                     DivBy du;
-                    du.b = sm.dg_b[i];
-                    du.y = sm.dg_y[i];
+                    du.b = pp == 0 ? dgb.x : pp == 1 ? dgb.y : pp == 2 ? dgb.z : dgb.w;
+                    du.y = pp == 0 ? dgy.x : pp == 1 ? dgy.y : pp == 2 ? dgy.z : dgy.w;
                     if (per_col) {          // act_order: every column has its own group (gptq.py:233-238)
                         sc = sm.pc_sc[srow * 128 + i];
                         zz = sm.pc_zz[srow * 128 + i];
                         ds.b = fmaxf(sc, GQ_EPS);
                         ds.y = sm.pc_y[srow * 128 + i];
+                        if (!SAFE) bad = bad || ds.y == 0.0f;
                     }
                     const float x = xg[pp];
                     const float t = __fadd_rn(x, zz);
-                    const float qv = kq_rint_clamp(SAFE ? ds.div(t) : ds.div_fast(t, bad), lo, hi);   // :247-254 (kq_quant)
+                    uint32_t qbits;
+                    const float qv = kq_rint_clamp_bits(SAFE ? ds.div(t) : div_chain(t, ds.b, ds.y, rng), lo, hi, qbits);   // :247-254 (kq_quant)
                     const float wq = kq_dequant(qv, sc, zz);                                          // :255-261
                     const float num = __fsub_rn(x, wq);
-                    const float err = SAFE ? du.div(num) : du.div_fast(num, bad);                     // :264
+                    const float err = SAFE ? du.div(num) : div_chain(num, du.b, du.y, rng);           // :264
                     // the group's remaining columns (the replicated copy): w -= fl(err * u), two roundings     :267
                     if (pp < 1) xg[1] = __fsub_rn(xg[1], __fmul_rn(err, ug.y));
                     if (pp < 2) xg[2] = __fsub_rn(xg[2], __fmul_rn(err, ug.z));
@@ -170,11 +179,10 @@ __device__ __noinline__ bool serial_block_impl(Smem &sm, int blk, int warp, int 
                     }
                     errs[pp] = err;                                                                   // :268
                     wqs[pp] = wq;                                                                     // :266
-                    code4 |= (uint32_t)(uint8_t)(int8_t)(int)qv << (8 * pp);                          // :263
+                    code4 = __byte_perm(code4, qbits, pp == 0 ? 0x3214 : pp == 1 ? 0x3240 : pp == 2 ? 0x3410 : 0x4210);   // :263
                 }
                 // outputs of the group's four columns (identical in the row's eight lanes): one lane stores them, 16 + 16 + 4 bytes
                 if (l8 == 0) {
-                    const int i0 = 32 * m + 4 * q;
                     *reinterpret_cast<float4 *>(et + i0) = make_float4(errs[0], errs[1], errs[2], errs[3]);
                     *reinterpret_cast<float4 *>(wqo + i0) = make_float4(wqs[0], wqs[1], wqs[2], wqs[3]);
                     *reinterpret_cast<uint32_t *>(cd + i0) = code4;
@@ -182,13 +190,18 @@ __device__ __noinline__ bool serial_block_impl(Smem &sm, int blk, int warp, int 
             }
         }
     }
-    return bad;
+    return bad || !rng.ok();
 }
 
 template <int QT>
 __device__ __forceinline__ void serial_block(Smem &sm, int blk, int warp, int lane, f2_t nz2, bool per_col) {
-    const bool bad = serial_block_impl<QT, false>(sm, blk, warp, lane, nz2, per_col);
-    if (__any_sync(0xffffffffu, bad)) serial_block_impl<QT, true>(sm, blk, warp, lane, nz2, per_col);   // rare: exact IEEE divisions
+    // (two instantiations of the fast path: the act_order tables cost four predicated instructions per column otherwise)
+    const bool bad = per_col ? serial_block_impl<QT, false, true>(sm, blk, warp, lane, nz2)
+                             : serial_block_impl<QT, false, false>(sm, blk, warp, lane, nz2);
+    if (__any_sync(0xffffffffu, bad)) {      // rare: exact IEEE divisions
+        if (per_col) serial_block_impl<QT, true, true>(sm, blk, warp, lane, nz2);
+        else serial_block_impl<QT, true, false>(sm, blk, warp, lane, nz2);
+    }
     __syncwarp();
     // the block's dequantised values replace the consumed columns of the tile (this warp's 4 rows)
     const int srow = warp * 4 + (lane >> 3), l8 = lane & 7;
@@ -268,6 +281,8 @@ __global__ void __launch_bounds__(NT, 1) gptq_layer_kernel(const LayerParams p) 
             const DivBy dv = DivBy::make(sm.u.Ud[tid * 128 + tid]);
             sm.dg_b[tid] = dv.b;
             sm.dg_y[tid] = dv.y;
+            const bool unsafe = __any_sync(0xffffffffu, dv.y == 0.0f);
+            if ((tid & 31) == 0) sm.dg_unsafe[tid >> 5] = unsafe ? 1 : 0;
         }
     };
     auto load_Uoff = [&](int c1) {   // U[c1:c1+128, c1+128:c1+256] -> Uoff (row-major), 16 x 16-byte cp.async per thread

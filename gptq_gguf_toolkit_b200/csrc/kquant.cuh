@@ -33,6 +33,16 @@ __device__ __forceinline__ float kq_rint_clamp(float v, float lo, float hi) {
     return clampf(__fsub_rn(__fadd_rn(v, magic), magic), lo, hi);
 }
 
+// The same, also returning the bit pattern of the clamped sum BEFORE the magic constant is taken off again: its low byte is the
+// two's-complement code byte of the result (1.5 * 2^23 = 0x4B400000 has a zero low byte), so callers pack codes with one PRMT
+// instead of F2I + shift + mask + or.
+__device__ __forceinline__ float kq_rint_clamp_bits(float v, float lo, float hi, uint32_t &bits) {
+    const float magic = 12582912.0f;
+    const float t = clampf(__fadd_rn(v, magic), __fadd_rn(magic, lo), __fadd_rn(magic, hi));
+    bits = __float_as_uint(t);
+    return __fsub_rn(t, magic);
+}
+
 // float((uint8(L) ** 2) mod 256) for an integer-valued L in [0, MAXQ]  (quant_utils.py:246: the codes are uint8, so the square wraps).
 // L*L is exact in fp32; up to MAXQ = 15 it never reaches 256, beyond that 256*floor(L*L/256) is taken off -- the floor by an
 // addition of 2^23 rounded towards zero -- so the sum s_l2 needs no float <-> int conversions.

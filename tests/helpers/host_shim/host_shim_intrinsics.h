@@ -14,6 +14,8 @@
 
 struct SearchParams { int nstep; float num[64]; };
 
+static inline uint32_t __float_as_uint(float x) { uint32_t u; std::memcpy(&u, &x, 4); return u; }
+static inline float __uint_as_float(uint32_t u) { float x; std::memcpy(&x, &u, 4); return x; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }

@@ -9,8 +9,15 @@
 #include <map>
 #include <utility>
 
-static inline uint32_t __float_as_uint(float x) { uint32_t u; std::memcpy(&u, &x, 4); return u; }
-static inline float __uint_as_float(uint32_t u) { float x; std::memcpy(&x, &u, 4); return x; }
+static inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
+static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+// PRMT: byte n of the result = byte (selector nibble n) of {x (bytes 0-3), y (bytes 4-7)}; the replicate-sign mode (nibble bit 3) is not used
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+    const uint64_t xy = (uint64_t)x | ((uint64_t)y << 32);
+    uint32_t r = 0;
+    for (int n = 0; n < 4; ++n) r |= (uint32_t)((xy >> (8 * ((s >> (4 * n)) & 7))) & 0xFF) << (8 * n);
+    return r;
+}
 static inline long long clock64() { return 0; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
 // cp.async as late as legal (see exact_update_host.cpp)
