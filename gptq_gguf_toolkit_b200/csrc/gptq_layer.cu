@@ -17,13 +17,8 @@
 #include "gemm_f16x3.cuh"
 #include "tile.cuh"
 #include "rank_update.cuh"
-#include "exact_update64.cuh"
 #include <cmath>
 #include <cstdlib>
-
-#ifndef GQ_EXACT_UPDATE64_DEFAULT
-#define GQ_EXACT_UPDATE64_DEFAULT 1
-#endif
 
 namespace {
 
@@ -58,35 +53,7 @@ __global__ void __launch_bounds__(NT, 2) exact_update_kernel(const LayerParams p
     exact_update_body(p, c, smem_raw);
 }
 
-// The same update with an 8 x 8 register tile per thread (exact_update64.cuh): 64 rows x 256 columns per CTA, weights and
-// accumulators in registers, one CTA per SM.  Bit-identical to exact_update_kernel (same chains per element).
-__global__ void __launch_bounds__(rk64::NT, 1) exact_update64_kernel(const LayerParams p, const int c) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    exact_update64_body(p, c, smem_raw);
-}
-
-// GQ_EXACT_UPDATE=32|64 (read once; gq_debug_exact_update_rows() switches at run time for tests and micro-benchmarks): which
-// trailing-update kernel the exact right-looking schedule launches.
-int g_exact_update64 = -1;
-bool exact_update_use64() {
-    if (g_exact_update64 < 0) {
-        const char *e = getenv("GQ_EXACT_UPDATE");
-        g_exact_update64 = e ? (e[0] == '6' ? 1 : 0) : GQ_EXACT_UPDATE64_DEFAULT;
-    }
-    return g_exact_update64 == 1;
-}
-
 int launch_exact_update(const LayerParams &p, int c, cudaStream_t st) {
-    if (exact_update_use64()) {
-        GQ_CHECK_CUDA(cudaFuncSetAttribute(exact_update64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rk64::SMEM_BYTES));
-        const int nwin = (p.d_col - c - GQ_QK_K) / GQ_QK_K;
-        if (nwin <= 0) return GQ_OK;
-        dim3 grid(nwin, (p.d_row + rk64::R - 1) / rk64::R);
-        exact_update64_kernel<<<grid, rk64::NT, rk64::SMEM_BYTES, st>>>(p, c);
-        gq_count_launches(1);
-        GQ_CHECK_CUDA(cudaGetLastError());
-        return GQ_OK;
-    }
     const size_t smem = (size_t)S * (US_FLOATS + ES_FLOATS) * sizeof(float);
     // per launch, like launch_layer: the attribute belongs to the current device's context, a process may use several
     GQ_CHECK_CUDA(cudaFuncSetAttribute(exact_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -135,9 +102,6 @@ unsigned long long *g_phase_clk = nullptr;
 // debug hook (not part of the reference-facing API): device array of 8 u64 that the column-loop kernel adds its
 // per-phase cycle counts to (thread 0 of every CTA); nullptr switches the counters off.
 extern "C" GQ_API void gq_debug_phase_clocks(unsigned long long *dev8) { g_phase_clk = dev8; }
-// debug hook: rows per CTA of the exact schedule's trailing-update kernel: 32 = exact_update_kernel (8 x 4 tile, two CTAs per SM),
-// 64 = exact_update64_kernel (8 x 8 tile, one CTA per SM), anything else = back to the default / GQ_EXACT_UPDATE
-extern "C" GQ_API void gq_debug_exact_update_rows(int rows) { g_exact_update64 = rows == 64 ? 1 : rows == 32 ? 0 : -1; }
 extern "C" GQ_API void gq_profile_enable(int on) { g_prof_on = on != 0; }
 // Synchronises, sums the recorded spans by kind (milliseconds, launch counts), clears the record.
 extern "C" GQ_API int gq_profile_read3(float ms[3], int counts[3]) {

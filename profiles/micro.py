@@ -100,31 +100,6 @@ def main():
                       f"split {pr['split_ms']:.2f} ms/{pr['split_launches']}, "
                       f"tcgen05 rank-k GEMMs {pr['rankk_gemm_ms']:.2f} ms/{pr['rankk_gemm_launches']} -> {rows * n * (n - 256) / max(pr['rankk_gemm_ms'], 1e-9) / 1e9:.0f} TFLOP/s", flush=True)
             os.environ.pop("GQ_FAST_GROUP", None)
-    if "updab" in what:
-        # A/B of the exact schedule's two trailing-update kernels (8 x 4 tile / 32 rows per CTA vs 8 x 8 tile / 64 rows per CTA)
-        import ctypes as C
-        from gptq_gguf_toolkit_b200 import _lib
-        lib = _lib.load()
-        lib.gq_debug_exact_update_rows.argtypes = [C.c_int]
-        lib.gq_debug_exact_update_rows.restype = None
-        for rows, n in ((512, 4096), (768, 4096), (1024, 4096), (3584, 4096), (4096, 4096), (6144, 4096), (14336, 4096), (28672, 4096),
-                        (512, 14336), (2048, 14336), (4096, 14336)):
-            U = torch.triu(torch.randn(n, n, device="cuda") * 0.01) + torch.eye(n, device="cuda")
-            W0 = torch.randn(rows, n, device="cuda") * 0.02
-            res = []
-            for tile in (32, 64):
-                lib.gq_debug_exact_update_rows(tile)
-                mn, _ = timed(lambda: ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16), warm=1, it=3)
-                ops.profile_enable(True)
-                ops.gptq_quantize(W0.clone(), U, 12, wdeq_dtype=torch.bfloat16)
-                pr = ops.profile_read()
-                ops.profile_enable(False)
-                fl = rows * n * (n - 256)
-                res.append(f"rows/CTA {tile}: layer {mn:.2f} ms, update launches {pr['rankk_gemm_ms']:.2f} ms/{pr['rankk_gemm_launches']} "
-                           f"-> {fl / max(pr['rankk_gemm_ms'], 1e-9) / 1e9:.1f} TFLOP/s, panels {pr['panel_ms']:.2f} ms")
-            lib.gq_debug_exact_update_rows(0)
-            print(f"updab {rows}x{n}: " + " | ".join(res), flush=True)
-            del U, W0
     if "schedules" in what:
         # the two bit-identical schedules of the exact arithmetic on row slices (what one rank of an N-GPU run launches)
         for rows, n in ((4096, 14336), (2048, 14336), (1024, 14336), (512, 14336), (4096, 4096), (512, 4096), (28672, 4096), (14336, 4096), (3584, 4096), (6144, 4096), (3072, 4096), (768, 4096)):

@@ -27,9 +27,8 @@ template <int N> static inline void cp_async_wait() {
 }
 static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 static inline float __fsub_rn(float a, float b) { return a - b; }
-alignas(16) unsigned char smem_raw[128 * 1024];       // the kernel's `extern __shared__ ... smem_raw[]`
+alignas(16) unsigned char smem_raw[80 * 1024];       // the kernel's `extern __shared__ ... smem_raw[]`
 #include "rank_update.cuh"          // the SHIPPED trailing-update body (exact_update_kernel) and rank_update<>
-#include "exact_update64.cuh"       // the SHIPPED 8 x 8-tile trailing update (exact_update64_kernel)
 namespace upd { struct Params { float *W; const float *U; int d_row, d_col; }; }
 
 // the shipped kernel: exact_update_kernel = exact_update_body<LayerParams> (csrc/gptq_layer.cu); 256 threads per CTA
@@ -39,16 +38,5 @@ extern "C" int run_exact_update_v1(float *W, const float *U, int d_row, int d_co
     if (nwin <= 0) return 0;
     upd::Params p{W, U, d_row, d_col};
     simt::launch(dim3(nwin, (d_row + rk::R - 1) / rk::R), dim3(rk::NT), [&]() { exact_update_body(p, c, smem_raw); });
-    return 0;
-}
-
-// the shipped 8 x 8-tile kernel: exact_update64_kernel = exact_update64_body<LayerParams>; 256 threads per CTA, 64 rows
-extern "C" int run_exact_update_v64(float *W, const float *U, int d_row, int d_col, int c) {
-    static_assert(rk64::SMEM_BYTES <= sizeof(smem_raw), "shared memory array too small");
-    const int nwin = (d_col - c - 256) / 256;
-    if (nwin <= 0) return 0;
-    upd::Params p{W, U, d_row, d_col};
-    cpa::reset();
-    simt::launch(dim3(nwin, (d_row + rk64::R - 1) / rk64::R), dim3(rk64::NT), [&]() { exact_update64_body(p, c, smem_raw); });
     return 0;
 }

@@ -103,34 +103,3 @@ def test_down_proj_slice_all_schedules_identical(ops, rows):
     # and the oracle on the first 32 rows (the CPU restatement needs ~10 s for this width)
     ref = orc.gptq_step(W[:32].cpu().numpy(), U.cpu().numpy(), 12)
     assert_five_equal([t[:32] for t in got["right"][:5]], ref[:5], "down slice vs oracle")
-
-
-@pytest.mark.parametrize("shape", [(100, 1280), (4096, 4096), (200, 14336)])
-def test_both_trailing_update_kernels_identical(ops, shape):
-    """The right-looking schedule's trailing update has two kernels of the same arithmetic: exact_update_kernel (8 x 4 register tile,
-    32 rows per CTA, two CTAs per SM) and exact_update64_kernel (8 x 8 tile, 64 rows per CTA, weights and accumulators in
-    registers; csrc/exact_update64.cuh).  Every output and the errors left in W must agree bit for bit (ragged row counts: 100 and
-    200 are not multiples of 64), and the default must be one of them."""
-    import ctypes as C
-    from gptq_gguf_toolkit_b200 import _lib
-    lib = _lib.load()
-    lib.gq_debug_exact_update_rows.argtypes = [C.c_int]
-    lib.gq_debug_exact_update_rows.restype = None
-    d_row, d_col = shape
-    g = torch.Generator(device="cuda").manual_seed(d_row + d_col)
-    W = torch.randn(d_row, d_col, device="cuda", generator=g) * 0.02
-    U = torch.triu(torch.randn(d_col, d_col, device="cuda", generator=g) * (0.3 / d_col ** 0.5))
-    U.diagonal().copy_(1.0 + 0.1 * torch.rand(d_col, device="cuda", generator=g))
-    got = {}
-    try:
-        for rows in (32, 64, 0):
-            lib.gq_debug_exact_update_rows(rows)
-            Wk = W.clone()
-            out = ops.gptq_quantize(Wk, U, 12, wdeq_dtype=torch.bfloat16, mode=_modes()["right"])
-            torch.cuda.synchronize()
-            got[rows] = tuple(out[:7]) + (Wk,)
-    finally:
-        lib.gq_debug_exact_update_rows(0)
-    for rows in (64, 0):
-        for a, b in zip(got[rows], got[32]):
-            assert torch.equal(a, b), f"{rows} vs 32"
