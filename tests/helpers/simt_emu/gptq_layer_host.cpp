@@ -125,3 +125,14 @@ extern "C" int run_gptq_layer_ex(int qtype, int right_looking, float *W, const f
     }
     return -1;
 }
+
+// ---- DivRange / div_chain (f32x2.cuh): the dividend bookkeeping of the column steps' fast divisions ----
+// ok_out[i] = DivRange that has seen only a[i] is still ok();  q_out[i] = div_chain(a[i], b, 1/b)
+extern "C" void run_div_chain(const float *a, int n, float b, int *ok_out, float *q_out) {
+    const DivBy d = DivBy::make(b);
+    for (int i = 0; i < n; ++i) {
+        DivRange rg;
+        q_out[i] = div_chain(a[i], d.b, d.y, rg);
+        ok_out[i] = rg.ok() ? 1 : 0;
+    }
+}

@@ -358,3 +358,28 @@ def test_shipped_simt_hessian_kernel_on_the_emulator(tmp_path_factory):
         n += 1
     assert np.array_equal(H, H.T), "H must be exactly symmetric"
     assert np.abs(H - want).max() <= 5e-5 * np.abs(want).max()
+
+
+def test_div_chain_range_bookkeeping(lib_layer):
+    """DivRange / div_chain (csrc/f32x2.cuh): the column steps' Markstein quotient is only proven equal to IEEE division for a zero
+    dividend or one inside (2^-60, 2^60); the two integer min / max accumulators must flag exactly the rest (the block is then re-run
+    with IEEE divisions), and inside the range the quotient must be the correctly rounded one."""
+    f = np.float32
+    safe = [0.0, -0.0, 1.0, -3.5, np.nextafter(f(2.0 ** 60), f(0)), -np.nextafter(f(2.0 ** 60), f(0)),
+            np.nextafter(f(2.0 ** -60), f(1)), -np.nextafter(f(2.0 ** -60), f(1)), 1e-10, 6e17]
+    unsafe = [2.0 ** 60, -(2.0 ** 60), 2.0 ** -60, -(2.0 ** -60), 1e-30, 1e-45, -1e-45, 3e38, np.inf, -np.inf, np.nan]
+    a = np.array(safe + unsafe, dtype=np.float32)
+    rng = np.random.default_rng(0)
+    a = np.concatenate([a, (rng.standard_normal(4096) * np.exp(8 * rng.standard_normal(4096))).astype(np.float32)])
+    ok = np.zeros(a.size, np.int32)
+    q = np.zeros(a.size, np.float32)
+    for b in (f(0.37), f(-1.7e-3), f(911.0)):
+        lib_layer.run_div_chain(a.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(a.size), C.c_float(b),
+                                ok.ctypes.data_as(C.POINTER(C.c_int)), q.ctypes.data_as(C.POINTER(C.c_float)))
+        aa = np.abs(a)
+        want_ok = (a == 0) | ((aa > f(2.0 ** -60)) & (aa < f(2.0 ** 60)))
+        assert np.array_equal(ok.astype(bool), want_ok), b
+        with np.errstate(all="ignore"):
+            ref = (a / b).astype(np.float32)
+        m = want_ok
+        assert np.array_equal(q[m], ref[m]), b            # as values: a zero quotient's sign is allowed to differ
