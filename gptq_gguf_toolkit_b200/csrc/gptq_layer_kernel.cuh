@@ -86,10 +86,12 @@ struct __align__(16) Smem {
 // (two roundings per element: f2_mul_nofuse then sub.rn.f32x2; the already consumed columns of the slots it touches see U's
 // zeros below the diagonal).
 // The two divisions of the dependent chain -- (x + z) / max(s, eps) and (x - w_q) / U[i,i] -- use reciprocals prepared
-// off the chain (DivBy, f32x2.cuh).  SAFE = false: branch-free (DivBy::div_fast, stores through a select-ed pointer);
-// returns true if some quotient was outside the range in which div_fast is proven exact -- the caller then reruns the
-// block with SAFE = true (IEEE fallback inside DivBy::div).  The block's initial values are read from Wt, its
-// dequantised values go to `Wq` (a separate buffer), so a rerun starts from unchanged inputs.
+// off the chain (DivBy, f32x2.cuh).  SAFE = false: branch-free Markstein quotients (div_chain) whose dividends are tracked by two
+// integer min / max accumulators (DivRange); returns true if a dividend left the range in which the quotient is proven to equal
+// the IEEE one, or a divisor has no checked reciprocal -- the caller then reruns the block with SAFE = true (IEEE fallback inside
+// DivBy::div).  The block's initial values are read from Wt, its dequantised values go to `Wq` (a separate buffer), so a rerun
+// starts from unchanged inputs.  per_col (act_order: every column has its own scale group) is a template parameter: the table
+// loads would otherwise sit, predicated off, in every column step.
 template <int QT, bool SAFE, bool per_col>
 __device__ __noinline__ bool serial_block_impl(Smem &sm, int blk, int warp, int lane, f2_t nz2) {
     constexpr int GS = Fmt<QT>::GS;
