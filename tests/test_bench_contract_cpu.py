@@ -51,3 +51,9 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["metric"] == "llama3_8b_q4k_quantize_wall_clock_s" and d["unit"] == "s"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the line's own step time is the bounded sample's wall time, not the extrapolated metric
+    assert d["cpu_baseline"]["extrapolated"] is True and 0 < d["ms_per_step"] < 600e3
+    assert set(("hessian", "prepare", "step", "forwards", "rtn")) <= set(d["cpu_baseline"]["sample_seconds"])
+    # both arms name the SAME workload: identical `config` objects
+    own = _run()
+    assert own["config"] == d["config"]
