@@ -98,3 +98,58 @@ def test_driver_on_other_families(monkeypatch, family):
             h.update(x)
         five = h.quantize(12)
         assert torch.equal(five[0], q.results[name]["qweight"]), name
+
+
+def _build_other(family):
+    import transformers
+    torch.manual_seed(0)
+    if family == "opt":       # LayerNorm, biases everywhere, learned positions, fc1 / fc2, blocks under model.decoder.layers
+        cfg = transformers.OPTConfig(vocab_size=512, hidden_size=256, ffn_dim=512, num_hidden_layers=2, num_attention_heads=4,
+                                     max_position_embeddings=128, word_embed_proj_dim=256, tie_word_embeddings=False)
+        return (transformers.OPTForCausalLM(cfg).float().eval(), r".*layers.*((q|k|v|out)_proj|fc1|fc2)$",
+                ["model.decoder.embed_tokens"], "model.decoder.layers", ["q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2"], 6)
+    # Phi-3: fused qkv_proj and gate_up_proj (no two layers share an input)
+    cfg = transformers.Phi3Config(vocab_size=512, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                                  num_key_value_heads=4, max_position_embeddings=128, pad_token_id=0, tie_word_embeddings=False)
+    return (transformers.Phi3ForCausalLM(cfg).float().eval(), r".*layers.*((qkv|o|gate_up|down)_proj)$",
+            ["model.embed_tokens"], "model.layers", ["qkv_proj", "o_proj", "gate_up_proj", "down_proj"], 4)
+
+
+@pytest.mark.parametrize("family", ["opt", "phi3"])
+def test_driver_on_other_module_layouts(monkeypatch, family):
+    """The reference selects layers by --quantizable_modules / --pre_block_modules / --block_modules / --post_block_modules
+    (quant.py:18-142), nothing in it is Llama-specific; neither may the driver's scheduling be (pass-1 early exit, Hessian sharing,
+    deferred last layer, fused forward pieces): OPT (other module names and block path, LayerNorm, biases) and Phi-3 (fused
+    projections).  Every selected layer is emitted once with the requested type, the weights left in the model are the
+    dequantisation of the emitted tensors, biases and norms are untouched, and the quantised model still runs."""
+    from tests import _oracle_backend as ob
+    ob.install(monkeypatch)
+    from gptq_gguf_toolkit_b200.quant_utils import GGMLQuantizationType as T
+    from gptq_gguf_toolkit_b200.quantizer import Quantizer
+
+    model, regex, pre, blocks, proj, per_block = _build_other(family)
+    pristine = {n: p.data.clone() for n, p in model.named_parameters()}
+    g = torch.Generator().manual_seed(1)
+    loader = [([], {"input_ids": torch.randint(1, 512, (1, 64), generator=g)}) for _ in range(4)]
+    qc = {k: T.Q4_K for k in proj}
+    qc.update(embed_tokens=T.Q6_K, lm_head=T.Q6_K)
+    qc[proj[-1]] = T.Q5_K
+    q = Quantizer(model, data_loader=loader, quantizable_modules=regex,
+                  quantizer_kwargs=dict(rel_damp=0.01, block_size=128, act_order=False, quant_scale="absmax",
+                                        static_groups=False, rmin=-1.0, rdelta=0.1, nstep=20, verbose=False),
+                  pre_block_modules=pre, block_modules=blocks, post_block_modules=["lm_head"],
+                  quant_non_block_modules=True, device="cpu", save_dir=None, keep_results=True, calibration_batch_size=2)
+    q.quantize(qc)
+    assert len(q.results) == 2 * per_block + 2
+    for n, d in q.results.items():
+        want = qc[n.split(".")[-1]]
+        assert int(d["q_type"]) == int(want), n
+        w = model.get_submodule(n).weight.data.numpy()
+        deq = orc.dequantize(int(d["q_type"]), d["qweight"].numpy(), d["super_group_scale"].numpy(), d["group_scale_quant"].numpy(),
+                             d["super_group_zero"].numpy(), d["group_zero_quant"].numpy())
+        assert np.array_equal(deq, w), n
+    changed = {n for n, p in model.named_parameters() if not torch.equal(p.data, pristine[n])}
+    assert changed == {n + ".weight" for n in q.results}, changed ^ {n + ".weight" for n in q.results}
+    with torch.no_grad():
+        out = model(input_ids=loader[0][1]["input_ids"]).logits
+    assert torch.isfinite(out).all()
