@@ -33,12 +33,14 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 METRIC = "llama3_8b_q4k_quantize_wall_clock_s"
-# ncu --set full, one launch of exact_update_kernel (profiles/r01_ncu_summary.md): dram__bytes_read.sum + dram__bytes_write.sum
-EXACT_UPDATE_DRAM_BYTES = 55.5e6
-EXACT_UPDATE_TRAFFIC_NOTE = ("ncu --set full of ONE launch (profiles/r01_final2_ncu_details_exact_update_kernel.csv): o_proj shape, "
-                             "4096 rows x 11 windows of 256 columns, 146.6 us, 53.2 MB read + 2.3 MB written; algorithmic "
+# ncu --set full, one launch of exact_update_kernel: dram__bytes_read.sum + dram__bytes_write.sum (round 2's capture,
+# profiles/r02/r02ag_ncu_details_colloop.csv; round 1's, profiles/r01_final2_ncu_details_exact_update_kernel.csv: 53.2 + 2.3 MB)
+EXACT_UPDATE_DRAM_BYTES = 54.7e6
+EXACT_UPDATE_TRAFFIC_NOTE = ("ncu --set full of ONE launch (profiles/r02/r02ag_ncu_details_colloop.csv): o_proj shape, "
+                             "4096 rows x 11 windows of 256 columns, 154.0 us, 53.2 MB read + 1.5 MB written; algorithmic "
                              "bytes of that launch 99.4 MB (W window read + written 92.3, E 4.2, U slab 2.9): the window was "
-                             "written by the previous launch and is still in the 126 MB L2")
+                             "written by the previous launch and is still in the 126 MB L2 (the write-back happens later); a constant "
+                             "of that capture, not a measurement of this run")
 REGEX = r".*layers.*((q|k|v|o|gate|up|down)_proj)$"
 
 WORKLOADS = {
