@@ -143,6 +143,26 @@ REFERENCE_MEASURED = {
 }
 
 
+_CPU_BLOCK = {}
+
+
+def _cpu_block(w):
+    """ONE decoder block of the workload's shape on the CPU, in the model's dtype (built once per process: constructing and
+    initialising 218 M parameters costs more than the sampled forward)."""
+    key = (w["hidden_size"], w["intermediate_size"], w["dtype"])
+    if key not in _CPU_BLOCK:
+        from transformers import LlamaConfig, LlamaModel
+        cfg = LlamaConfig(**{k: w[k] for k in ("hidden_size", "intermediate_size", "num_attention_heads", "num_key_value_heads",
+                                               "max_position_embeddings")}, num_hidden_layers=1, vocab_size=1024)
+        old = torch.get_default_dtype()
+        torch.set_default_dtype(getattr(torch, w["dtype"]))
+        try:
+            _CPU_BLOCK[key] = LlamaModel(cfg).eval()
+        finally:
+            torch.set_default_dtype(old)
+    return _CPU_BLOCK[key]
+
+
 def cpu_reference_sample(w, threads: int):
     """Times a bounded sample (~10-30 s of CPU work, depending on the host's cores) and extrapolates each phase by its algorithmic
     work to the whole model.  Returns (whole_model_hot_path_seconds, detail).  Sample: 16 sequences of H.addmm_ and one Cholesky chain at every distinct
@@ -202,22 +222,13 @@ def cpu_reference_sample(w, threads: int):
     #    linearly to 2 passes x n_seq sequences x all blocks (the attention's quadratic term is under-counted: kinder to the CPU)
     t_f, L_f = None, min(L, 512)
     try:
-        from transformers import LlamaConfig, LlamaModel
-        cfg = LlamaConfig(**{k: w[k] for k in ("hidden_size", "intermediate_size", "num_attention_heads", "num_key_value_heads",
-                                               "max_position_embeddings")}, num_hidden_layers=1, vocab_size=1024)
-        old = torch.get_default_dtype()
-        torch.set_default_dtype(getattr(torch, w["dtype"]))
-        try:
-            blk = LlamaModel(cfg).eval()
-        finally:
-            torch.set_default_dtype(old)
+        blk = _cpu_block(w)
         ids = torch.randint(0, 1024, (1, L_f), generator=g)
         with torch.no_grad():
             blk(input_ids=ids)
             t0 = time.perf_counter()
             blk(input_ids=ids)
             t_f = time.perf_counter() - t0
-        del blk
     except Exception as ex:  # noqa: BLE001
         detail["forward_sample_failed"] = f"{type(ex).__name__}: {str(ex)[:120]}"
     fwd = (t_f or 0.0) * (L / L_f) * nseq * 2 * nblk
